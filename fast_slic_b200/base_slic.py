@@ -1,0 +1,281 @@
+"""Python surface of the reference, re-hosted on the CUDA engine.
+
+Mirrors /root/reference/fast_slic/base_slic.py:3-62 (BaseSlic / Slic: same kwargs, defaults,
+properties, return dtype) and the Cython ``SlicModel`` (/root/reference/cfast_slic.pyx:15-260,
+attributes cfast_slic.pxd:104-120).  Only the default integer-distance path of the north star is
+implemented; the float-distance / LSC / preemptive variants raise NotImplementedError.
+"""
+import json
+
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import CLUSTER_DTYPE, Engine, require_cuda
+
+ARCH_NAME = "cuda/sm_100a"
+_SUPPORTED_ARCHS = (ARCH_NAME,)
+
+_engines = {}
+
+
+def get_engine(H, W, K, batch=1, device=0):
+    """Contexts are cached and reused (the reference rebuilds one per call, cfast_slic.pyx:171-197)."""
+    key = (int(device), int(H), int(W), int(K))
+    eng = _engines.get(key)
+    if eng is None or eng.max_batch < batch:
+        if eng is not None:
+            eng.close()
+        eng = Engine(H, W, K, max_batch=batch, device=device)
+        _engines[key] = eng
+    return eng
+
+
+def clear_engine_cache():
+    for e in _engines.values():
+        e.close()
+    _engines.clear()
+
+
+def get_supported_archs():
+    """== cfast_slic.get_supported_archs (cfast_slic.pyx:358-369)."""
+    return list(_SUPPORTED_ARCHS)
+
+
+def is_supported_arch(arch_name):
+    return arch_name in _SUPPORTED_ARCHS
+
+
+def _check_image(image):
+    # the Cython signature `const uint8_t [:, :, ::1]` raises ValueError on dtype / ndim / contiguity
+    if not isinstance(image, np.ndarray):
+        image = np.asarray(image)
+    if image.dtype != np.uint8:
+        raise ValueError("Buffer dtype mismatch, expected 'const uint8_t' but got %r" % (image.dtype.name,))
+    if image.ndim != 3:
+        raise ValueError("Buffer has wrong number of dimensions (expected 3, got %d)" % image.ndim)
+    if not image.flags["C_CONTIGUOUS"]:
+        raise ValueError("ndarray is not C-contiguous")
+    if image.shape[2] != 3:
+        raise ValueError("nchan != 3")  # cfast_slic.pyx:125,153
+    return image
+
+
+class SlicModel(object):
+    """== cfast_slic.SlicModel: owns the Cluster[K] array (host copy, 32-byte records)."""
+
+    def __init__(self, num_components, arch_name=ARCH_NAME, real_dist=False):
+        if not is_supported_arch(arch_name):
+            raise NotImplementedError("Unsupported arch " + repr(arch_name))  # cfast_slic.pyx:21-22
+        if num_components >= 65534:
+            raise ValueError("num_components cannot exceed 65534")  # cfast_slic.pyx:24-25
+        elif num_components <= 0:
+            raise ValueError("num_components should be a non-negative integer")  # cfast_slic.pyx:26-27
+        self._num_components = int(num_components)
+        self.num_threads = -1
+        self.arch_name = arch_name
+        self.real_dist = real_dist
+        self.real_dist_type = "standard"
+        self.convert_to_lab = False
+        self.float_color = True
+        self.debug_mode = False
+        self._clusters = np.zeros(self._num_components, CLUSTER_DTYPE)
+        self.initialized = False
+        self.preemptive = False
+        self.preemptive_thres = 0.05
+        self.manhattan_spatial_dist = True
+        self.last_timing_report = None
+        self.last_recorder_report = None
+        self.device = 0
+
+    @property
+    def num_components(self):
+        return self._num_components
+
+    def copy(self):
+        """cfast_slic.pyx:45-49 (copies the clusters and the initialized flag only)."""
+        result = SlicModel(self._num_components)
+        result._clusters = self._clusters.copy()
+        result.initialized = self.initialized
+        return result
+
+    @property
+    def clusters(self):
+        """cfast_slic.pyx:51-66."""
+        return [
+            dict(number=int(c["number"]), yx=(float(c["y"]), float(c["x"])),
+                 color=(float(c["r"]), float(c["g"]), float(c["b"])), num_members=int(c["num_members"]))
+            for c in self._clusters
+        ]
+
+    @clusters.setter
+    def clusters(self, clusters):
+        """cfast_slic.pyx:68-98: yx -> uint16, colour -> uint8, number = index."""
+        new = np.zeros(len(clusters), CLUSTER_DTYPE)
+        for i, d in enumerate(clusters):
+            y, x = d["yx"]
+            r, g, b = d["color"]
+            new[i]["number"] = i
+            new[i]["y"] = np.uint16(int(y))
+            new[i]["x"] = np.uint16(int(x))
+            new[i]["r"] = np.uint8(int(r))
+            new[i]["g"] = np.uint8(int(g))
+            new[i]["b"] = np.uint8(int(b))
+            new[i]["num_members"] = np.uint32(int(d["num_members"]))
+            new[i]["is_active"] = 1
+            new[i]["is_updatable"] = 1
+        self._clusters = new
+        self._num_components = len(clusters)
+        self.initialized = True
+
+    @property
+    def cluster_array(self):
+        """The raw Cluster[K] records as a numpy structured array (a view, not part of the reference API)."""
+        return self._clusters
+
+    def _unsupported(self):
+        if self.real_dist:
+            raise NotImplementedError("float-distance variants (real_dist) are outside the CUDA hot path")
+        if self.preemptive:
+            raise NotImplementedError("preemptive=True is outside the CUDA hot path")
+        if not self.manhattan_spatial_dist:
+            raise NotImplementedError("manhattan_spatial_dist=False is outside the CUDA hot path")
+
+    def initialize(self, image):
+        """cfast_slic.pyx:124-147."""
+        image = _check_image(image)
+        require_cuda()
+        H, W, _ = image.shape
+        eng = get_engine(H, W, self._num_components, 1, self.device)
+        self._clusters = eng.initialize_clusters_host(image[None])[0]
+        self.initialized = True
+
+    def iterate(self, image, max_iter, compactness, min_size_factor, subsample_stride):
+        """cfast_slic.pyx:150-260: returns int16[H, W]."""
+        if not self.initialized:
+            raise RuntimeError("Slic model is not initialized")  # cfast_slic.pyx:151
+        image = _check_image(image)
+        self._unsupported()
+        require_cuda()
+        H, W, _ = image.shape
+        eng = get_engine(H, W, self._num_components, 1, self.device)
+        params = eng.params(compactness, min_size_factor, subsample_stride, self.convert_to_lab, max_iter,
+                            collect_timing=True)
+        clusters = np.ascontiguousarray(self._clusters)[None]
+        labels = eng.iterate_host(image[None], clusters, params)
+        self._clusters = clusters[0]
+        ms = eng.stage_ms()
+        self.last_timing_report = json.dumps({
+            "name": "iterate", "duration": int(ms["iterate"] * 1000),
+            "children": [{"name": n, "duration": int(ms[n] * 1000), "children": []}
+                         for n in ("cielab_conversion", "assign", "update", "full_assign", "enforce_connectivity")],
+        })
+        self.last_recorder_report = b'{"snapshots":[]}'
+        return labels[0]
+
+
+class BaseSlic(object):
+    """== fast_slic.base_slic.BaseSlic (/root/reference/fast_slic/base_slic.py:3-59)."""
+    arch_name = "__TODO__"
+
+    def __init__(self, num_components=400, slic_model=None, compactness=10, min_size_factor=0.25,
+                 subsample_stride=3, convert_to_lab=True, preemptive=False, preemptive_thres=0.05,
+                 manhattan_spatial_dist=True, debug_mode=False, num_threads=-1):
+        self.compactness = compactness
+        self.subsample_stride = subsample_stride
+        self.min_size_factor = min_size_factor
+        self._slic_model = slic_model and slic_model.copy() or self.make_slic_model(num_components)
+        self._last_assignment = None
+        self.convert_to_lab = convert_to_lab
+        self._slic_model.preemptive = preemptive
+        self._slic_model.preemptive_thres = preemptive_thres
+        self._slic_model.manhattan_spatial_dist = manhattan_spatial_dist
+        self._slic_model.num_threads = num_threads
+        self._slic_model.debug_mode = debug_mode
+
+    @property
+    def convert_to_lab(self):
+        return self._slic_model.convert_to_lab
+
+    @convert_to_lab.setter
+    def convert_to_lab(self, v):
+        self._slic_model.convert_to_lab = v
+
+    @property
+    def slic_model(self):
+        return self._slic_model
+
+    @property
+    def last_assignment(self):
+        return self._last_assignment
+
+    def iterate(self, image, max_iter=10):
+        if not self._slic_model.initialized:
+            self._slic_model.initialize(image)
+        assignment = self._slic_model.iterate(image, max_iter, self.compactness, self.min_size_factor,
+                                              self.subsample_stride)
+        self._last_assignment = assignment
+        return assignment
+
+    @property
+    def num_components(self):
+        return self._slic_model.num_components
+
+    def make_slic_model(self, num_components):
+        return SlicModel(num_components, self.arch_name)
+
+    # ---- batch extension (no counterpart in the reference: it has no batch API) -------------------
+    def iterate_batch(self, images, max_iter=10, clusters=None, return_clusters=False):
+        """Independent images [B,H,W,3] (uint8, numpy or cuda tensor) -> int16 labels [B,H,W] of the same kind.
+
+        Every image gets its own freshly seeded cluster set (or `clusters` to warm start, a [B,K]
+        structured array / [B,K,32] uint8 cuda tensor); the single-image state of this object is untouched.
+        """
+        self._slic_model._unsupported()
+        require_cuda()
+        K = self._slic_model.num_components
+        is_tensor = isinstance(images, torch.Tensor)
+        B, H, W = int(images.shape[0]), int(images.shape[1]), int(images.shape[2])
+        if images.shape[3] != 3:
+            raise ValueError("nchan != 3")
+        device = images.device.index if is_tensor else self._slic_model.device
+        eng = get_engine(H, W, K, B, device)
+        params = eng.params(self.compactness, self.min_size_factor, self.subsample_stride, self.convert_to_lab,
+                            max_iter)
+        if is_tensor:
+            if clusters is None:
+                clusters = eng.initialize_clusters(images)
+            labels = eng.iterate(images, clusters, params)
+        else:
+            images = np.ascontiguousarray(images)
+            if images.dtype != np.uint8:
+                raise ValueError("images must be uint8")
+            if clusters is None:
+                clusters = eng.initialize_clusters_host(images)
+            labels = eng.iterate_host(images, clusters, params)
+        return (labels, clusters) if return_clusters else labels
+
+
+class Slic(BaseSlic):
+    """Drop-in for fast_slic.Slic / fast_slic.avx2.SlicAvx2 (identical results; base_slic.py:61-62, avx2.py:10-11)."""
+    arch_name = ARCH_NAME
+
+
+SlicCuda = Slic
+
+
+def enforce_connectivity(assignments, min_threshold):
+    """== cfast_slic.enforce_connectivity (cfast_slic.pyx:371-396): int16[H,W] in place, K = max label + 1."""
+    if not isinstance(assignments, np.ndarray) or assignments.dtype != np.int16 or assignments.ndim != 2 \
+            or not assignments.flags["C_CONTIGUOUS"]:
+        raise ValueError("assignments must be a C-contiguous int16[H, W] array")
+    require_cuda()
+    H, W = assignments.shape
+    lab = assignments.view(np.uint16)
+    valid = lab[lab != 0xFFFF]
+    K = (int(valid.max()) if valid.size else 0) + 1
+    eng = get_engine(H, W, max(min(K, 65533), 1), 1, 0)
+    t = torch.from_numpy(assignments).to(eng.device)[None].contiguous()
+    eng.enforce_connectivity(t, K, int(min_threshold))
+    assignments[...] = t[0].cpu().numpy()
+    return assignments

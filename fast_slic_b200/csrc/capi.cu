@@ -1,0 +1,519 @@
+// fast_slic_b200/csrc/capi.cu -- host orchestration + the extern "C" boundary (include/fslic_b200.h).
+//
+// Plays the role of BaseContext<uint16_t>::iterate (/root/reference/src/context.cpp:109-197) and of
+// the Cython glue that drives it (cfast_slic.pyx:124-197): owns the scratch buffers, sequences the
+// kernels on one stream, never touches the CPU for the data path.
+#include <math.h>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "assign.cuh"
+#include "cca.cuh"
+#include "common.cuh"
+#include "lab.cuh"
+
+static thread_local std::string g_err;
+static int set_err(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e__ = (call);                                                                     \
+        if (e__ != cudaSuccess)                                                                       \
+            return set_err(FSLIC_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__));         \
+    } while (0)
+
+struct fslic_ctx {
+    int device = 0, H = 0, W = 0, K = 0, maxB = 0, S = 0, N = 0;
+    int num_sms = 148;
+    // tables
+    uint16_t *d_gamma = nullptr, *d_labtbl = nullptr;
+    LabConsts lc;
+    // assign state
+    uint32_t* quad = nullptr;      // [B][N]   Lab quad image
+    uint16_t* labels = nullptr;    // [B][N]   pre-CCA labels
+    CInfo* cinfo = nullptr;        // [B][K]
+    uint32_t* acc = nullptr;       // [B][K][6]
+    int* cell_start = nullptr;     // [B][ncell+1]
+    int* cell_items = nullptr;     // [B][K]
+    uint16_t* sptable = nullptr;   // linear spatial patch
+    int* overflow = nullptr;       // [1 + maxB*ntiles_max]
+    int G = 1, cellW = 1, cellH = 1, ncell = 1;
+    size_t overflow_cap = 0;
+    // cca state (sized for cca_batch images at a time)
+    int cca_batch = 1;
+    int* par = nullptr;            // [Bc][N]
+    uint32_t* aux = nullptr;       // [Bc][N]  area at root pixel, then component number
+    int* cleader = nullptr;        // [Bc][N]
+    uint32_t* carea = nullptr;     // [Bc][N]
+    uint16_t* cnew = nullptr;      // [Bc][N]
+    uint16_t* fin = nullptr;       // [Bc][N]
+    int* blkcnt = nullptr;         // [Bc][nblk]
+    int* blkoff = nullptr;         // [Bc][nblk]
+    CcaCounters* counters = nullptr;  // [Bc]
+    unsigned long long* heap = nullptr;  // [Bc][Kheap]
+    int heap_K = 0;
+    // staging for the host entry points
+    uint8_t *d_img = nullptr, *h_img = nullptr;
+    fslic_cluster *d_cl = nullptr, *h_cl = nullptr;
+    uint16_t *d_lab = nullptr, *h_lab = nullptr;
+    cudaStream_t own_stream = nullptr;
+    // timing
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    float stage_ms[FSLIC_T_COUNT] = {0, 0, 0, 0, 0, 0};
+    int last_launches = 0;
+    int max_smem_optin = 0;
+};
+
+extern "C" const char* fslic_b200_last_error(void) { return g_err.c_str(); }
+extern "C" const char* fslic_b200_version(void) { return "fast_slic_b200 0.1 (sm_100a)"; }
+extern "C" int fslic_b200_sizeof_cluster(void) { return (int)sizeof(fslic_cluster); }
+extern "C" int fslic_b200_get_S(const fslic_ctx* ctx) { return ctx ? ctx->S : -1; }
+extern "C" int fslic_b200_launches_last_iterate(const fslic_ctx* ctx) { return ctx ? ctx->last_launches : -1; }
+
+// ---- Lab tables: FastCIELabCvt ctor, /root/reference/src/cielab.h:297-305 ----------------------
+// _srgb_gamma_tbl (cielab.h:22-279) is the sRGB inverse companding curve documented at
+// cielab.h:12-20; it is regenerated here from that formula (bit-identical, checked in tests over the
+// whole 2^24 colour cube against the compiled reference).
+static void build_lab_tables(std::vector<uint16_t>& gamma, std::vector<uint16_t>& labtbl, LabConsts& lc) {
+    static const float C[9] = {0.43395633f, 0.37621531f, 0.18984309f, 0.2126729f, 0.7151522f,
+                               0.072175f,   0.01775782f, 0.1094756f,  0.87283638f};
+    gamma.resize(256);
+    labtbl.resize(8193);
+    for (int i = 0; i < 256; i++) {
+        const double v = i / 255.0;
+        const double X = (v <= 0.04045) ? v / 12.92 : pow((v + 0.055) / 1.055, 2.4);
+        gamma[i] = (uint16_t)(int)((float)X * 8192);
+    }
+    for (int i = 0; i < 9; i++) lc.Cb[i] = (int)roundf(C[i] * 65536);
+    for (int i = 0; i <= 8192; i++) {
+        const float v = (float)i / 8192;
+        const float lo = 7.787f * v + 0.137931f;
+        const float hi = powf(v, 0.333333f);
+        labtbl[i] = (uint16_t)(int)roundf(((v > 0.008856f) ? hi : lo) * 8192);
+    }
+}
+
+template <typename T>
+static cudaError_t dalloc(T** p, size_t count) {
+    return cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T) + 256);
+}
+
+extern "C" int fslic_b200_destroy(fslic_ctx* c) {
+    if (!c) return FSLIC_OK;
+    cudaSetDevice(c->device);
+    void* ptrs[] = {c->d_gamma, c->d_labtbl, c->quad,   c->labels,  c->cinfo,  c->acc,    c->cell_start,
+                    c->cell_items, c->sptable, c->overflow, c->par,  c->aux,    c->cleader, c->carea,
+                    c->cnew,    c->fin,      c->blkcnt, c->blkoff,  c->counters, c->heap, c->d_img,
+                    c->d_cl,    c->d_lab};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (c->h_img) cudaFreeHost(c->h_img);
+    if (c->h_cl) cudaFreeHost(c->h_cl);
+    if (c->h_lab) cudaFreeHost(c->h_lab);
+    for (auto& e : c->ev)
+        if (e) cudaEventDestroy(e);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+    return FSLIC_OK;
+}
+
+extern "C" int fslic_b200_create(int device, int H, int W, int K, int max_batch, fslic_ctx** out) {
+    if (!out) return set_err(FSLIC_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (H <= 0 || W <= 0) return set_err(FSLIC_EINVAL, "H and W must be positive");
+    if (K <= 0) return set_err(FSLIC_EINVAL, "num_components should be a non-negative integer");  // cfast_slic.pyx:26-27
+    if (K >= 65534) return set_err(FSLIC_EINVAL, "num_components cannot exceed 65534");              // cfast_slic.pyx:24-25
+    if (max_batch <= 0) return set_err(FSLIC_EINVAL, "max_batch must be positive");
+    if ((long)H * W >= (1L << 30)) return set_err(FSLIC_EINVAL, "image too large (H*W must be < 2^30)");
+    if (H > 32767 || W > 32767) return set_err(FSLIC_EINVAL, "H and W must fit int16 (the reference truncates centres to int16)");
+    CK(cudaSetDevice(device));
+    fslic_ctx* c = new (std::nothrow) fslic_ctx();
+    if (!c) return set_err(FSLIC_ENOMEM, "out of host memory");
+    c->device = device;
+    c->H = H; c->W = W; c->K = K; c->maxB = max_batch; c->N = H * W;
+    c->S = (int)(int16_t)sqrt((double)(H * W / K));  // context.h:60 (integer division first)
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
+        c->num_sms = prop.multiProcessorCount;
+        c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    }
+    const size_t B = (size_t)max_batch, N = (size_t)c->N;
+#define CKC(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            std::string m = std::string(#call) + ": " + cudaGetErrorString(e__);                   \
+            fslic_b200_destroy(c);                                                                 \
+            return set_err(e__ == cudaErrorMemoryAllocation ? FSLIC_ENOMEM : FSLIC_ECUDA, m);      \
+        }                                                                                          \
+    } while (0)
+    std::vector<uint16_t> gamma, labtbl;
+    build_lab_tables(gamma, labtbl, c->lc);
+    CKC(dalloc(&c->d_gamma, 256));
+    CKC(dalloc(&c->d_labtbl, 8200));
+    CKC(cudaMemcpy(c->d_gamma, gamma.data(), 256 * 2, cudaMemcpyHostToDevice));
+    CKC(cudaMemcpy(c->d_labtbl, labtbl.data(), 8193 * 2, cudaMemcpyHostToDevice));
+
+    // candidate cell grid: pitch G >= max(S,1), at most ~16K cells so the histogram fits in smem
+    int G = c->S > 0 ? c->S : 1;
+    while ((long)ceil_div(H, G) * ceil_div(W, G) > 16000) G++;
+    c->G = G; c->cellW = ceil_div(W, G); c->cellH = ceil_div(H, G); c->ncell = c->cellW * c->cellH;
+
+    CKC(dalloc(&c->quad, B * N));
+    CKC(dalloc(&c->labels, B * N));
+    CKC(dalloc(&c->cinfo, B * K));
+    CKC(dalloc(&c->acc, B * K * 6));
+    CKC(cudaMemset(c->acc, 0, B * K * 6 * sizeof(uint32_t)));
+    CKC(dalloc(&c->cell_start, B * (c->ncell + 1)));
+    CKC(dalloc(&c->cell_items, B * K));
+    CKC(dalloc(&c->sptable, (size_t)256 * 1024));  // up to 512 KB of patch (only <= smem-sized ones are used)
+    // worst-case tile count: full pass with the smallest tile height (R = 1 -> 4 rows)
+    c->overflow_cap = B * (size_t)ceil_div(W, AS_WX * 32) * (size_t)ceil_div(H, AS_WY) + 1;
+    CKC(dalloc(&c->overflow, c->overflow_cap + 1));
+
+    // CCA scratch: 22 B/pixel/image; cap the resident set at ~12 GB
+    const size_t per_img = N * 22 + 4096;
+    size_t bc = (12ull << 30) / per_img;
+    if (bc < 1) bc = 1;
+    if (bc > B) bc = B;
+    c->cca_batch = (int)bc;
+    const int nblk = ceil_div(c->N, CCA_BLOCK);
+    CKC(dalloc(&c->par, bc * N));
+    CKC(dalloc(&c->aux, bc * N));
+    CKC(dalloc(&c->cleader, bc * N));
+    CKC(dalloc(&c->carea, bc * N));
+    CKC(dalloc(&c->cnew, bc * N));
+    CKC(dalloc(&c->fin, bc * N));
+    CKC(dalloc(&c->blkcnt, bc * nblk));
+    CKC(dalloc(&c->blkoff, bc * nblk));
+    CKC(dalloc(&c->counters, bc));
+    c->heap_K = 65536;
+    CKC(dalloc(&c->heap, bc * (size_t)c->heap_K));
+    for (auto& e : c->ev) CKC(cudaEventCreate(&e));
+    CKC(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+
+    // opt in to large dynamic shared memory once
+    CKC(cudaFuncSetAttribute(k_assign_tiles<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin - 20 * 1024));
+    CKC(cudaFuncSetAttribute(k_assign_tiles<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin - 20 * 1024));
+    CKC(cudaFuncSetAttribute(k_assign_tiles<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin - 20 * 1024));
+    CKC(cudaFuncSetAttribute(k_assign_tiles<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin - 20 * 1024));
+    CKC(cudaFuncSetAttribute(k_cca_select, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin - 40 * 1024));
+    CKC(cudaFuncSetAttribute(k_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+    *out = c;
+    return FSLIC_OK;
+}
+
+static int check_batch(fslic_ctx* c, int batch) {
+    if (!c) return set_err(FSLIC_EINVAL, "ctx is NULL");
+    if (batch <= 0 || batch > c->maxB) return set_err(FSLIC_EINVAL, "batch out of range for this context");
+    return FSLIC_OK;
+}
+
+extern "C" int fslic_b200_initialize_clusters(fslic_ctx* c, const uint8_t* d_images, fslic_cluster* d_clusters,
+                                              int batch, void* stream) {
+    int rc = check_batch(c, batch);
+    if (rc) return rc;
+    CK(cudaSetDevice(c->device));
+    dim3 grid(ceil_div(c->K, 128), batch);
+    k_init_clusters<<<grid, 128, 0, (cudaStream_t)stream>>>(d_images, d_clusters, c->H, c->W, c->K, batch);
+    CK(cudaGetLastError());
+    return FSLIC_OK;
+}
+
+static int launch_lab(fslic_ctx* c, const uint8_t* d_images, uint32_t* quad, int batch, int convert_to_lab,
+                      cudaStream_t st) {
+    const long npix = (long)batch * c->N;
+    long blocks = (npix / 4 + 255) / 256;
+    const long cap = (long)c->num_sms * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    k_rgb_to_quad<<<(int)blocks, 256, 0, st>>>(d_images, quad, npix, c->d_gamma, c->d_labtbl, c->lc, convert_to_lab);
+    CK(cudaGetLastError());
+    return FSLIC_OK;
+}
+
+extern "C" int fslic_b200_rgb_to_quad(fslic_ctx* c, const uint8_t* d_images, uint8_t* d_quad_out, int batch,
+                                      int convert_to_lab, void* stream) {
+    int rc = check_batch(c, batch);
+    if (rc) return rc;
+    CK(cudaSetDevice(c->device));
+    return launch_lab(c, d_images, reinterpret_cast<uint32_t*>(d_quad_out), batch, convert_to_lab, (cudaStream_t)stream);
+}
+
+// ---- connectivity enforcement over `batch` images, chunked by cca_batch -------------------------
+static int run_cca(fslic_ctx* c, const uint16_t* d_in, uint16_t* d_out, int batch, int K, int thres, cudaStream_t st,
+                   int* launches) {
+    const int N = c->N;
+    CcaParams cp;
+    cp.H = c->H; cp.W = c->W; cp.N = N; cp.K = K; cp.thres = thres;
+    cp.nblk = ceil_div(N, CCA_BLOCK);
+    const size_t heap_bytes = (size_t)K * 8;
+    cp.heap_in_smem = heap_bytes <= (size_t)(c->max_smem_optin - 40 * 1024);
+    if (K > c->heap_K) return set_err(FSLIC_EINVAL, "K too large for the selection heap");
+    for (int b0 = 0; b0 < batch; b0 += c->cca_batch) {
+        const int nb = (batch - b0 < c->cca_batch) ? (batch - b0) : c->cca_batch;
+        const uint16_t* in = d_in + (size_t)b0 * N;
+        uint16_t* out = d_out + (size_t)b0 * N;
+        CK(cudaMemsetAsync(c->counters, 0, sizeof(CcaCounters) * nb, st));
+        dim3 g(cp.nblk, nb);
+        k_ccl_init<<<g, CCA_BLOCK, 0, st>>>(cp, in, c->par, c->aux);
+        k_ccl_merge<<<g, CCA_BLOCK, 0, st>>>(cp, in, c->par);
+        k_ccl_flatten<<<g, CCA_BLOCK, 0, st>>>(cp, in, c->par, c->aux, c->blkcnt);
+        k_scan_blocks<<<nb, 1024, 0, st>>>(c->blkcnt, c->blkoff, cp.nblk, cp.nblk, nullptr, 0, 1,
+                                           &c->counters[0].ncomp, (int)(sizeof(CcaCounters) / sizeof(int)));
+        k_ccl_number<<<g, CCA_BLOCK, 0, st>>>(cp, c->par, c->aux, c->blkoff, c->cleader, c->carea, c->counters);
+        k_cca_select<<<nb, 1024, cp.heap_in_smem ? heap_bytes : 0, st>>>(cp, c->carea, c->counters, c->heap);
+        k_kept_count<<<g, CCA_BLOCK, 0, st>>>(cp, c->carea, c->counters, c->blkcnt);
+        k_scan_blocks<<<nb, 1024, 0, st>>>(c->blkcnt, c->blkoff, cp.nblk, 0, &c->counters[0].ncomp,
+                                           (int)(sizeof(CcaCounters) / sizeof(int)), CCA_BLOCK,
+                                           &c->counters[0].nkept, (int)(sizeof(CcaCounters) / sizeof(int)));
+        k_kept_label<<<g, CCA_BLOCK, 0, st>>>(cp, c->carea, c->counters, c->blkoff, c->cnew);
+        dim3 ga(ceil_div(N, 256), nb);
+        k_cca_absorb<<<ga, 256, 0, st>>>(cp, c->par, c->aux, c->cleader, c->cnew, c->counters, c->fin);
+        int ob = ceil_div(N, 256);
+        if (ob > c->num_sms * 32) ob = c->num_sms * 32;
+        dim3 go(ob, nb);
+        k_cca_output<<<go, 256, 0, st>>>(cp, c->par, c->fin, out);
+        CK(cudaGetLastError());
+        if (launches) *launches += 11;
+    }
+    return FSLIC_OK;
+}
+
+extern "C" int fslic_b200_enforce_connectivity(fslic_ctx* c, uint16_t* d_labels, int batch, int K, int min_threshold,
+                                               void* stream) {
+    int rc = check_batch(c, batch);
+    if (rc) return rc;
+    if (K <= 0) return FSLIC_OK;  // context.cpp:17
+    CK(cudaSetDevice(c->device));
+    return run_cca(c, d_labels, d_labels, batch, K, min_threshold, (cudaStream_t)stream, nullptr);
+}
+
+extern "C" int fslic_b200_debug_heap_select(fslic_ctx* c, const int32_t* d_area, int n, int middle, uint8_t* d_kept,
+                                            void* stream) {
+    if (!c) return set_err(FSLIC_EINVAL, "ctx is NULL");
+    if (middle > c->heap_K || middle < 1 || n < 1) return set_err(FSLIC_EINVAL, "bad n/middle");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemsetAsync(d_kept, 0, n, (cudaStream_t)stream));
+    k_debug_heap_select<<<1, 1024, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint32_t*>(d_area), n, middle,
+                                                             d_kept, c->heap);
+    CK(cudaGetLastError());
+    return FSLIC_OK;
+}
+
+// ---- one assign pass (fast tiles kernel + generic fallback) ---------------------------------------
+struct PassGeom {
+    int R;
+    bool fast;
+    int OY, OX, TS, tbl_elems;
+    size_t smem;
+};
+
+static PassGeom pass_geometry(const fslic_ctx* c, int stride) {
+    PassGeom g;
+    const int S = c->S;
+    g.R = 4;
+    g.OX = S + 31;
+    g.OY = S + stride * (g.R - 1);
+    g.TS = 2 * g.OX + 2;  // even row pitch
+    g.tbl_elems = (2 * g.OY + 1) * g.TS;
+    g.smem = align_up((size_t)g.tbl_elems * 2, 16);
+    g.fast = g.smem <= (size_t)(c->max_smem_optin - 24 * 1024) && g.tbl_elems <= 256 * 1024;
+    return g;
+}
+
+static int run_assign_pass(fslic_ctx* c, int batch, int stride, int rem, int cfg_stride, int fresh_from, bool update,
+                           float coef, cudaStream_t st, int* launches) {
+    const PassGeom g = pass_geometry(c, stride);
+    AssignParams ap;
+    ap.H = c->H; ap.W = c->W; ap.K = c->K; ap.S = c->S; ap.B = batch;
+    ap.stride = stride; ap.rem = rem;
+    ap.nsub = (c->H - rem + stride - 1) / stride;
+    if (ap.nsub <= 0) return FSLIC_OK;
+    ap.cfg_stride = cfg_stride; ap.fresh_from = fresh_from;
+    ap.G = c->G; ap.cellW = c->cellW; ap.cellH = c->cellH; ap.ncell = c->ncell;
+    ap.OY = g.OY; ap.OX = g.OX; ap.TS = g.TS; ap.tbl_elems = g.tbl_elems;
+    ap.tiles_x = ceil_div(c->W, AS_WX * 32);
+    ap.tiles_y = ceil_div(ap.nsub, AS_WY * g.R);
+    ap.ntiles = ap.tiles_x * ap.tiles_y;
+    ap.coef = coef;
+    const long total = (long)ap.ntiles * batch;
+    if (g.fast) {
+        k_build_sptable<<<64, 256, 0, st>>>(c->sptable, c->S, g.OY, g.OX, g.TS, coef);
+        CK(cudaMemsetAsync(c->overflow, 0, sizeof(int), st));
+        int occ = 1;
+        if (update)
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_assign_tiles<4, true>, AS_THREADS, g.smem);
+        else
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_assign_tiles<4, false>, AS_THREADS, g.smem);
+        if (occ < 1) occ = 1;
+        long grid = (long)c->num_sms * occ;
+        if (grid > total) grid = total;
+        if (update)
+            k_assign_tiles<4, true><<<(int)grid, AS_THREADS, g.smem, st>>>(ap, c->quad, c->labels, c->cinfo, c->cell_start,
+                                                                           c->cell_items, c->acc, c->sptable, c->overflow);
+        else
+            k_assign_tiles<4, false><<<(int)grid, AS_THREADS, g.smem, st>>>(ap, c->quad, c->labels, c->cinfo, c->cell_start,
+                                                                            c->cell_items, c->acc, c->sptable, c->overflow);
+        // overflowed tiles (normally none): generic kernel over the recorded list, grid sized for a modest count
+        int og = (int)(total < 4096 ? total : 4096);
+        if (update)
+            k_assign_generic<true><<<og, 256, 0, st>>>(ap, c->quad, c->labels, c->cinfo, c->cell_start, c->cell_items,
+                                                       c->acc, c->overflow, g.R);
+        else
+            k_assign_generic<false><<<og, 256, 0, st>>>(ap, c->quad, c->labels, c->cinfo, c->cell_start, c->cell_items,
+                                                        c->acc, c->overflow, g.R);
+        if (launches) *launches += 3;
+    } else {
+        if (update)
+            k_assign_generic<true><<<(int)total, 256, 0, st>>>(ap, c->quad, c->labels, c->cinfo, c->cell_start,
+                                                               c->cell_items, c->acc, nullptr, g.R);
+        else
+            k_assign_generic<false><<<(int)total, 256, 0, st>>>(ap, c->quad, c->labels, c->cinfo, c->cell_start,
+                                                                c->cell_items, c->acc, nullptr, g.R);
+        if (launches) *launches += 1;
+    }
+    CK(cudaGetLastError());
+    return FSLIC_OK;
+}
+
+static int run_prepare(fslic_ctx* c, fslic_cluster* d_clusters, int batch, int first, int finalize, cudaStream_t st,
+                       int* launches) {
+    PrepParams pp;
+    pp.H = c->H; pp.W = c->W; pp.K = c->K; pp.S = c->S; pp.T = 2 * c->S + 32;
+    pp.G = c->G; pp.cellW = c->cellW; pp.cellH = c->cellH; pp.ncell = c->ncell;
+    pp.first = first; pp.finalize = finalize; pp.last = 0;
+    const size_t smem = (size_t)(c->ncell + 2) * sizeof(int);
+    k_prepare<<<batch, 1024, smem, st>>>(pp, d_clusters, c->acc, c->quad, c->cinfo, c->cell_start, c->cell_items);
+    CK(cudaGetLastError());
+    if (launches) *launches += 1;
+    return FSLIC_OK;
+}
+
+extern "C" int fslic_b200_iterate(fslic_ctx* c, const uint8_t* d_images, fslic_cluster* d_clusters, uint16_t* d_labels,
+                                  int batch, const fslic_params* p, void* stream) {
+    int rc = check_batch(c, batch);
+    if (rc) return rc;
+    if (!p) return set_err(FSLIC_EINVAL, "params is NULL");
+    if (p->subsample_stride <= 0 || p->subsample_stride > 255) return set_err(FSLIC_EINVAL, "subsample_stride must be in 1..255");
+    if (p->max_iter < 0) return set_err(FSLIC_EINVAL, "max_iter must be >= 0");
+    if (!(p->compactness >= 0.f)) return set_err(FSLIC_EINVAL, "compactness must be >= 0");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int S = c->S;
+    const int color_shift = p->convert_to_lab ? 1 : 0;  // cielab.h:25,352 / context.cpp:127
+    // BaseContext::set_spatial_patch, context.cpp:25-26 (same float operations, same order)
+    float coef = 1.0f / ((float)S / p->compactness);
+    coef *= (float)(1 << color_shift);
+    if (S > 0 && !(coef * (float)(2 * S) < (float)(FSLIC_BIGSP - 766)))
+        return set_err(FSLIC_ERANGE, "compactness too large: the u16 distance of the reference would overflow");
+    if (S == 0) coef = 0.f;  // 1/(0/compactness) = inf in the reference; with S == 0 only m = 0 is ever used -> inf*0 = NaN -> (u16) UB; use 0
+    int launches = 0;
+    const bool timing = p->collect_timing != 0;
+    if (timing) CK(cudaEventRecord(c->ev[0], st));
+    rc = launch_lab(c, d_images, c->quad, batch, p->convert_to_lab, st);
+    if (rc) return rc;
+    launches++;
+    if (timing) CK(cudaEventRecord(c->ev[1], st));
+    const int stride = p->subsample_stride;
+    int rem = 0;
+    for (int it = 0; it < p->max_iter; it++) {
+        rc = run_prepare(c, d_clusters, batch, it == 0, it > 0, st, &launches);
+        if (rc) return rc;
+        rc = run_assign_pass(c, batch, stride, rem, stride, it, true, coef, st, &launches);
+        if (rc) return rc;
+        rem = (rem + 1) % stride;
+    }
+    if (timing) CK(cudaEventRecord(c->ev[2], st));
+    rc = run_prepare(c, d_clusters, batch, p->max_iter == 0, p->max_iter > 0, st, &launches);
+    if (rc) return rc;
+    rc = run_assign_pass(c, batch, 1, 0, stride, p->max_iter < stride ? p->max_iter : stride, false, coef, st, &launches);
+    if (rc) return rc;
+    if (timing) CK(cudaEventRecord(c->ev[3], st));
+    const int thres = (int)round((double)(S * S) * (double)p->min_size_factor);  // context.cpp:16
+    rc = run_cca(c, c->labels, d_labels, batch, c->K, thres, st, &launches);
+    if (rc) return rc;
+    if (timing) {
+        CK(cudaEventRecord(c->ev[4], st));
+        CK(cudaEventSynchronize(c->ev[4]));
+        float ms;
+        CK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1])); c->stage_ms[FSLIC_T_CIELAB] = ms;
+        CK(cudaEventElapsedTime(&ms, c->ev[1], c->ev[2])); c->stage_ms[FSLIC_T_ASSIGN] = ms;
+        c->stage_ms[FSLIC_T_UPDATE] = 0.f;  // fused into assign
+        CK(cudaEventElapsedTime(&ms, c->ev[2], c->ev[3])); c->stage_ms[FSLIC_T_FULL_ASSIGN] = ms;
+        CK(cudaEventElapsedTime(&ms, c->ev[3], c->ev[4])); c->stage_ms[FSLIC_T_CCA] = ms;
+        CK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[4])); c->stage_ms[FSLIC_T_TOTAL] = ms;
+    }
+    c->last_launches = launches;
+    return FSLIC_OK;
+}
+
+extern "C" int fslic_b200_stage_ms(fslic_ctx* c, float* out_ms, int count) {
+    if (!c || !out_ms) return set_err(FSLIC_EINVAL, "NULL argument");
+    for (int i = 0; i < count && i < FSLIC_T_COUNT; i++) out_ms[i] = c->stage_ms[i];
+    return FSLIC_OK;
+}
+
+extern "C" int fslic_b200_debug_stages(fslic_ctx* c, uint8_t* d_quad_out, uint16_t* d_precca_out, int batch,
+                                       void* stream) {
+    int rc = check_batch(c, batch);
+    if (rc) return rc;
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d_quad_out) CK(cudaMemcpyAsync(d_quad_out, c->quad, (size_t)batch * c->N * 4, cudaMemcpyDeviceToDevice, st));
+    if (d_precca_out) CK(cudaMemcpyAsync(d_precca_out, c->labels, (size_t)batch * c->N * 2, cudaMemcpyDeviceToDevice, st));
+    return FSLIC_OK;
+}
+
+// ---- host-buffer entry points (what the reference-facing plugin calls) --------------------------
+static int ensure_staging(fslic_ctx* c) {
+    if (c->d_img) return FSLIC_OK;
+    const size_t B = (size_t)c->maxB, N = (size_t)c->N;
+    CK(dalloc(&c->d_img, B * N * 3));
+    CK(dalloc(&c->d_cl, B * c->K));
+    CK(dalloc(&c->d_lab, B * N));
+    CK(cudaMallocHost(reinterpret_cast<void**>(&c->h_img), B * N * 3));
+    CK(cudaMallocHost(reinterpret_cast<void**>(&c->h_cl), B * c->K * sizeof(fslic_cluster)));
+    CK(cudaMallocHost(reinterpret_cast<void**>(&c->h_lab), B * N * 2));
+    return FSLIC_OK;
+}
+
+extern "C" int fslic_b200_initialize_clusters_host(fslic_ctx* c, const uint8_t* h_images, fslic_cluster* h_clusters,
+                                                   int batch) {
+    int rc = check_batch(c, batch);
+    if (rc) return rc;
+    CK(cudaSetDevice(c->device));
+    rc = ensure_staging(c);
+    if (rc) return rc;
+    cudaStream_t st = c->own_stream;
+    const size_t ib = (size_t)batch * c->N * 3, cb = (size_t)batch * c->K * sizeof(fslic_cluster);
+    CK(cudaMemcpyAsync(c->d_img, h_images, ib, cudaMemcpyHostToDevice, st));
+    rc = fslic_b200_initialize_clusters(c, c->d_img, c->d_cl, batch, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h_clusters, c->d_cl, cb, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return FSLIC_OK;
+}
+
+extern "C" int fslic_b200_iterate_host(fslic_ctx* c, const uint8_t* h_images, fslic_cluster* h_clusters,
+                                       uint16_t* h_labels, int batch, const fslic_params* p) {
+    int rc = check_batch(c, batch);
+    if (rc) return rc;
+    CK(cudaSetDevice(c->device));
+    rc = ensure_staging(c);
+    if (rc) return rc;
+    cudaStream_t st = c->own_stream;
+    const size_t ib = (size_t)batch * c->N * 3, cb = (size_t)batch * c->K * sizeof(fslic_cluster),
+                 lb = (size_t)batch * c->N * 2;
+    CK(cudaMemcpyAsync(c->d_img, h_images, ib, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->d_cl, h_clusters, cb, cudaMemcpyHostToDevice, st));
+    rc = fslic_b200_iterate(c, c->d_img, c->d_cl, c->d_lab, batch, p, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h_labels, c->d_lab, lb, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_clusters, c->d_cl, cb, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return FSLIC_OK;
+}

@@ -1,0 +1,142 @@
+"""Device-side engine: one `Engine` == one fslic_ctx (fixed H, W, K, max batch) on one GPU.
+
+Host logic only -- tensors in, tensors out; all arithmetic happens in libfslic_b200.so.
+PyTorch is used for device memory and streams, nothing else.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Params, check
+
+CLUSTER_DTYPE = np.dtype(
+    [("y", "<f4"), ("x", "<f4"), ("r", "<f4"), ("g", "<f4"), ("b", "<f4"), ("a", "<f4"),
+     ("number", "<u2"), ("is_active", "u1"), ("is_updatable", "u1"), ("num_members", "<u4")]
+)  # == Cluster, /root/reference/src/fast-slic-common.h:10-23
+assert CLUSTER_DTYPE.itemsize == 32
+
+
+def _stream_ptr(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("fast_slic_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+class Engine:
+    def __init__(self, H, W, K, max_batch=1, device=0):
+        require_cuda()
+        self.H, self.W, self.K, self.max_batch = int(H), int(W), int(K), int(max_batch)
+        self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+        self._L = _lib.lib()
+        h = C.c_void_p()
+        check(self._L.fslic_b200_create(self.device.index, self.H, self.W, self.K, self.max_batch, C.byref(h)))
+        self._h = h
+        self.S = self._L.fslic_b200_get_S(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.fslic_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- helpers -------------------------------------------------------------------------------
+    def _check_images(self, images):
+        if images.dtype != torch.uint8 or images.dim() != 4 or images.shape[1:] != (self.H, self.W, 3):
+            raise ValueError("images must be uint8 [B, %d, %d, 3]" % (self.H, self.W))
+        if not images.is_contiguous():
+            raise ValueError("images must be contiguous")
+        if images.device != self.device:
+            raise ValueError("images must live on %s" % self.device)
+        if images.shape[0] > self.max_batch:
+            raise ValueError("batch larger than the engine's max_batch")
+
+    def new_clusters(self, batch):
+        return torch.zeros((batch, self.K, 32), dtype=torch.uint8, device=self.device)
+
+    @staticmethod
+    def params(compactness=10.0, min_size_factor=0.25, subsample_stride=3, convert_to_lab=True, max_iter=10,
+               collect_timing=False):
+        return Params(float(compactness), float(min_size_factor), int(subsample_stride), int(bool(convert_to_lab)),
+                      int(max_iter), int(bool(collect_timing)))
+
+    # -- device entry points -------------------------------------------------------------------
+    def initialize_clusters(self, images, clusters=None):
+        self._check_images(images)
+        B = images.shape[0]
+        if clusters is None:
+            clusters = self.new_clusters(B)
+        check(self._L.fslic_b200_initialize_clusters(self._h, images.data_ptr(), clusters.data_ptr(), B,
+                                                     _stream_ptr(self.device)))
+        return clusters
+
+    def iterate(self, images, clusters, params, labels=None):
+        """images u8[B,H,W,3] (cuda), clusters u8[B,K,32] (cuda, updated in place) -> labels u16 as int16[B,H,W]."""
+        self._check_images(images)
+        B = images.shape[0]
+        if labels is None:
+            labels = torch.empty((B, self.H, self.W), dtype=torch.int16, device=self.device)
+        check(self._L.fslic_b200_iterate(self._h, images.data_ptr(), clusters.data_ptr(), labels.data_ptr(), B,
+                                         C.byref(params), _stream_ptr(self.device)))
+        return labels
+
+    def enforce_connectivity(self, labels, K, min_threshold):
+        """In place on int16/uint16 labels [B,H,W] (cuda)."""
+        B = labels.shape[0]
+        check(self._L.fslic_b200_enforce_connectivity(self._h, labels.data_ptr(), B, int(K), int(min_threshold),
+                                                      _stream_ptr(self.device)))
+        return labels
+
+    def rgb_to_quad(self, images, convert_to_lab=True):
+        self._check_images(images)
+        B = images.shape[0]
+        quad = torch.empty((B, self.H, self.W, 4), dtype=torch.uint8, device=self.device)
+        check(self._L.fslic_b200_rgb_to_quad(self._h, images.data_ptr(), quad.data_ptr(), B, int(convert_to_lab),
+                                             _stream_ptr(self.device)))
+        return quad
+
+    def debug_stages(self, batch):
+        quad = torch.empty((batch, self.H, self.W, 4), dtype=torch.uint8, device=self.device)
+        pre = torch.empty((batch, self.H, self.W), dtype=torch.int16, device=self.device)
+        check(self._L.fslic_b200_debug_stages(self._h, quad.data_ptr(), pre.data_ptr(), batch,
+                                              _stream_ptr(self.device)))
+        return quad, pre
+
+    def debug_heap_select(self, area, middle):
+        area = area.to(self.device, torch.int32).contiguous()
+        kept = torch.empty(area.numel(), dtype=torch.uint8, device=self.device)
+        check(self._L.fslic_b200_debug_heap_select(self._h, area.data_ptr(), area.numel(), int(middle),
+                                                   kept.data_ptr(), _stream_ptr(self.device)))
+        return kept
+
+    # -- host entry points (numpy in / numpy out, copies inside) ---------------------------------
+    def initialize_clusters_host(self, images_np):
+        B = images_np.shape[0]
+        clusters = np.zeros((B, self.K), CLUSTER_DTYPE)
+        check(self._L.fslic_b200_initialize_clusters_host(self._h, images_np.ctypes.data, clusters.ctypes.data, B))
+        return clusters
+
+    def iterate_host(self, images_np, clusters_np, params, labels_np=None):
+        B = images_np.shape[0]
+        if labels_np is None:
+            labels_np = np.empty((B, self.H, self.W), np.int16)
+        check(self._L.fslic_b200_iterate_host(self._h, images_np.ctypes.data, clusters_np.ctypes.data,
+                                              labels_np.ctypes.data, B, C.byref(params)))
+        return labels_np
+
+    def stage_ms(self):
+        out = (C.c_float * 6)()
+        check(self._L.fslic_b200_stage_ms(self._h, out, 6))
+        return dict(zip(_lib.STAGE_NAMES, [float(v) for v in out]))
+
+    def launches_last_iterate(self):
+        return int(self._L.fslic_b200_launches_last_iterate(self._h))

@@ -1,0 +1,57 @@
+"""Seeded inputs shared by the CPU and GPU parity tests."""
+import numpy as np
+
+from oracle.oracle import synthetic_image
+
+
+def make_image(kind, H, W, seed=1, sigma=12.0):
+    if kind == "syn":
+        return synthetic_image(H, W, seed, sigma)
+    if kind == "flat":
+        return np.full((H, W, 3), 77, np.uint8)
+    if kind == "noise":
+        return np.random.RandomState(seed).randint(0, 256, (H, W, 3)).astype(np.uint8)
+    if kind == "blocks":  # piecewise-constant patches: many exact distance ties
+        rng = np.random.RandomState(seed)
+        small = rng.randint(0, 4, (H // 8 + 1, W // 8 + 1, 3)) * 60
+        return np.ascontiguousarray(np.kron(small, np.ones((8, 8, 1)))[:H, :W].astype(np.uint8))
+    raise ValueError(kind)
+
+
+# name, kind, H, W, K, kwargs
+PIPELINE_CASES = [
+    ("A_640x480_K200", "syn", 480, 640, 200, {}),
+    ("odd_97x131_K37_msf.1", "syn", 97, 131, 37, dict(min_size_factor=0.1)),
+    ("flat_97x131_K37", "flat", 97, 131, 37, dict(min_size_factor=0.5)),
+    ("noise_120x160_K48_msf0", "noise", 120, 160, 48, dict(min_size_factor=0.0)),
+    ("noise_120x160_K48_msf.25", "noise", 120, 160, 48, dict(min_size_factor=0.25)),
+    ("blocks_200x300_K150_msf0", "blocks", 200, 300, 150, dict(min_size_factor=0.0)),
+    ("thin_300x10_K4", "syn", 300, 10, 4, {}),
+    ("thin_10x400_K5_it2", "syn", 10, 400, 5, dict(max_iter=2)),
+    ("thin_301x17_K6_it1", "syn", 301, 17, 6, dict(max_iter=1)),
+    ("one_cluster_64x64", "syn", 64, 64, 1, {}),
+    ("rgb_path_150x200_K300", "syn", 150, 200, 300, dict(convert_to_lab=False, min_size_factor=0.0)),
+    ("compact37.5_150x200_K30", "syn", 150, 200, 30, dict(compactness=37.5)),
+    ("compact1_180x240_K150", "syn", 180, 240, 150, dict(compactness=1.0)),
+    ("stride2_it1", "syn", 150, 200, 30, dict(subsample_stride=2, max_iter=1)),
+    ("stride1_it3", "syn", 90, 120, 20, dict(subsample_stride=1, max_iter=3)),
+    ("stride5_it7", "syn", 150, 200, 60, dict(subsample_stride=5, max_iter=7)),
+    ("it0", "syn", 120, 160, 40, dict(max_iter=0)),
+    ("bigS_generic_300x400_K2", "syn", 300, 400, 2, {}),
+    ("dense_K_64x64_K1500", "noise", 64, 64, 1500, dict(min_size_factor=0.0)),
+    ("speckle_240x320_K100_msf0", "syn", 240, 320, 100, dict(min_size_factor=0.0, sigma=40.0)),
+]
+
+BIG_CASES = [
+    ("B_1280x720_K1600_msf0", "syn", 720, 1280, 1600, dict(min_size_factor=0.0)),
+    ("B_1280x720_K1600_msf.1_s40", "syn", 720, 1280, 1600, dict(min_size_factor=0.1, sigma=40.0)),
+    ("C_1920x1080_K2000_msf0", "syn", 1080, 1920, 2000, dict(min_size_factor=0.0)),
+]
+
+
+def split_kwargs(kw):
+    kw = dict(kw)
+    sigma = kw.pop("sigma", 12.0)
+    args = dict(max_iter=10, compactness=10.0, min_size_factor=0.25, subsample_stride=3, convert_to_lab=True)
+    args.update(kw)
+    return sigma, args

@@ -1,0 +1,186 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle, bit-exact.
+
+Tolerance: 0 for label maps (pre- and post-CCA), the Lab quad image and every Cluster field
+(they are integers on this path).
+"""
+import numpy as np
+import pytest
+import torch
+
+from cases import BIG_CASES, PIPELINE_CASES, make_image, split_kwargs
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(H, W, K, B=1):
+    from fast_slic_b200 import get_engine
+    return get_engine(H, W, K, B, 0)
+
+
+def _run_cuda(img, K, args, iterate_twice=False):
+    H, W, _ = img.shape
+    eng = _engine(H, W, K)
+    t = torch.from_numpy(img).cuda()[None].contiguous()
+    cl = eng.initialize_clusters(t)
+    init = cl.cpu().numpy().copy()
+    p = eng.params(args["compactness"], args["min_size_factor"], args["subsample_stride"], args["convert_to_lab"],
+                   args["max_iter"])
+    lab = eng.iterate(t, cl, p)
+    if iterate_twice:
+        lab = eng.iterate(t, cl, p)
+    quad, pre = eng.debug_stages(1)
+    torch.cuda.synchronize()
+    return init, lab[0].cpu().numpy().view(np.uint16), quad[0].cpu().numpy(), pre[0].cpu().numpy().view(np.uint16), \
+        cl[0].cpu().numpy()
+
+
+def _run_oracle(port, img, K, args, iterate_twice=False):
+    cl = port.initialize(img, K)
+    init = cl.copy()
+    out, quad, pre = port.iterate(img, cl, args["max_iter"], args["compactness"], args["min_size_factor"],
+                                  args["subsample_stride"], args["convert_to_lab"], stages=True)
+    if iterate_twice:
+        out, quad, pre = port.iterate(img, cl, args["max_iter"], args["compactness"], args["min_size_factor"],
+                                      args["subsample_stride"], args["convert_to_lab"], stages=True)
+    return init, out, quad, pre, cl
+
+
+def _compare(name, got, want):
+    ginit, glab, gquad, gpre, gcl = got
+    winit, wlab, wquad, wpre, wcl = want
+    assert ginit.tobytes() == winit.tobytes(), name + ": initialize_clusters differs"
+    assert (gquad == wquad).all(), name + ": quad image differs (%d px)" % (gquad != wquad).any(-1).sum()
+    assert (gpre == wpre).all(), name + ": pre-CCA labels differ (%d px)" % (gpre != wpre).sum()
+    gc = gcl.view(wcl.dtype).reshape(-1)
+    for f in ("y", "x", "r", "g", "b", "num_members", "number", "is_active", "is_updatable"):
+        assert (gc[f] == wcl[f]).all(), name + ": cluster field %s differs" % f
+    assert (glab == wlab).all(), name + ": final labels differ (%d px)" % (glab != wlab).sum()
+
+
+@pytest.mark.parametrize("case", PIPELINE_CASES, ids=[c[0] for c in PIPELINE_CASES])
+def test_pipeline_parity(port, case):
+    name, kind, H, W, K, kw = case
+    sigma, args = split_kwargs(kw)
+    img = make_image(kind, H, W, seed=7, sigma=sigma)
+    _compare(name, _run_cuda(img, K, args), _run_oracle(port, img, K, args))
+
+
+@pytest.mark.parametrize("case", BIG_CASES, ids=[c[0] for c in BIG_CASES])
+def test_pipeline_parity_big(port, case):
+    name, kind, H, W, K, kw = case
+    sigma, args = split_kwargs(kw)
+    img = make_image(kind, H, W, seed=11, sigma=sigma)
+    _compare(name, _run_cuda(img, K, args), _run_oracle(port, img, K, args))
+
+
+def test_warm_start_second_iterate(port):
+    img = make_image("syn", 200, 260, seed=3)
+    _, args = split_kwargs({})
+    _compare("warm", _run_cuda(img, 90, args, iterate_twice=True), _run_oracle(port, img, 90, args, iterate_twice=True))
+
+
+def test_batch_matches_single(port):
+    H, W, K, B = 180, 240, 70, 5
+    imgs = np.stack([make_image("syn" if b % 2 == 0 else "noise", H, W, seed=20 + b) for b in range(B)])
+    from fast_slic_b200 import Slic
+    s = Slic(num_components=K, min_size_factor=0.1)
+    labels, clusters = s.iterate_batch(torch.from_numpy(imgs).cuda(), return_clusters=True)
+    labels = labels.cpu().numpy().view(np.uint16)
+    labels_h, clusters_h = s.iterate_batch(imgs, return_clusters=True)
+    for b in range(B):
+        cl = port.initialize(imgs[b], K)
+        want = port.iterate(imgs[b], cl, 10, 10.0, 0.1, 3, True)
+        assert (labels[b] == want).all(), "device batch image %d" % b
+        assert (labels_h[b].view(np.uint16) == want).all(), "host batch image %d" % b
+        assert clusters[b].cpu().numpy().tobytes() == cl.tobytes() == clusters_h[b].tobytes()
+
+
+def test_lab_full_colour_cube(port):
+    """All 2^24 colours as one 4096x4096 image, against the oracle (which is pinned to the reference)."""
+    v = np.arange(1 << 24, dtype=np.uint32)
+    img = np.stack([(v >> 16) & 255, (v >> 8) & 255, v & 255], -1).astype(np.uint8).reshape(4096, 4096, 3)
+    eng = _engine(4096, 4096, 1000)
+    got = eng.rgb_to_quad(torch.from_numpy(img).cuda()[None]).cpu().numpy()[0]
+    want = port.rgb_to_quad(img, True)
+    assert (got == want).all()
+    import hashlib
+    cube = np.ascontiguousarray(got[..., :3]).tobytes()
+    assert hashlib.sha256(cube).hexdigest() == "016250467c2bd57f2ef75f61bb0571a9ab8d6558f69eca0ac0831d20db948624"
+    from fast_slic_b200 import clear_engine_cache
+    clear_engine_cache()
+
+
+@pytest.mark.parametrize("n,middle,maxarea", [(50, 7, 3), (1000, 100, 4), (5000, 1600, 6), (20000, 300, 2),
+                                              (100000, 4000, 50), (4097, 4096, 3), (300, 300, 5), (9000, 1, 4)])
+def test_heap_select_device_vs_stl(port, n, middle, maxarea):
+    rng = np.random.RandomState(n + middle)
+    area = rng.randint(1, maxarea + 1, n).astype(np.int32)
+    area[rng.randint(0, n, max(1, n // 50))] += rng.randint(0, 1000, max(1, n // 50)).astype(np.int32)
+    eng = _engine(64, 64, 8)
+    kept = eng.debug_heap_select(torch.from_numpy(area), middle).cpu().numpy()
+    want = port.stl_partial_sort(area, middle)
+    assert (np.nonzero(kept)[0] == want).all()
+
+
+def test_enforce_connectivity_known_answer():
+    """The reference's only live gtest vector: src/cpptest/test_cca.cpp:178-204."""
+    from fast_slic_b200 import enforce_connectivity
+    x = 9
+    lab = np.array([[0, 0, 0, 0, 0], [1, 1, x, 0, 0], [1, x, 0, x, 4], [2, 2, x, x, 4], [2, 3, 3, 3, 3]], np.int16)
+    out = enforce_connectivity(lab.copy(), 0)
+    assert out[1, 2] == 0 and out[2, 1] == 0 and out[2, 2] == 0
+    assert out[2, 3] == 9 and out[3, 2] == 9 and out[3, 3] == 9
+
+
+@pytest.mark.parametrize("H,W,nlab,thres,seed", [(60, 80, 6, 0, 1), (60, 80, 6, 5, 2), (100, 33, 3, 12, 3),
+                                                 (257, 515, 40, 30, 4), (64, 64, 2, 1, 5), (1, 700, 4, 3, 6),
+                                                 (700, 1, 4, 3, 7), (720, 1280, 1600, 58, 8)])
+def test_enforce_connectivity_random(port, H, W, nlab, thres, seed):
+    from fast_slic_b200 import enforce_connectivity
+    rng = np.random.RandomState(seed)
+    small = rng.randint(0, nlab, (H // 3 + 1, W // 3 + 1))
+    lab = np.kron(small, np.ones((3, 3), int))[:H, :W]
+    noise = rng.rand(H, W) < 0.15
+    lab[noise] = rng.randint(0, nlab, noise.sum())
+    lab = np.ascontiguousarray(lab.astype(np.int16))
+    K = int(lab.max()) + 1
+    want = port.enforce_connectivity(lab.view(np.uint16), K, thres)
+    got = enforce_connectivity(lab.copy(), thres).view(np.uint16)
+    assert (got == want).all(), "%d px differ" % (got != want).sum()
+
+
+def test_python_surface_matches_reference_api():
+    """Mirrors /root/reference/test/test_slic.py:41-65."""
+    from fast_slic_b200 import Slic
+    x = np.zeros([480, 640, 3], np.uint8)
+    slic = Slic(num_components=100)
+    out = slic.iterate(x)
+    assert out.dtype == np.int16 and out.shape == (480, 640)
+    for i, cluster in enumerate(slic.slic_model.clusters):
+        assert cluster["number"] == i
+        assert isinstance(cluster, dict)
+        assert len(cluster["yx"]) == 2 and isinstance(cluster["yx"], tuple)
+        assert len(cluster["color"]) == 3 and isinstance(cluster["color"], tuple)
+        assert isinstance(cluster["num_members"], int)
+    orig = slic.slic_model.clusters
+    slic.slic_model.clusters = orig[:10]
+    assert len(slic.slic_model.clusters) == 10
+    assert slic.slic_model.clusters == orig[:10]
+    assert slic.slic_model.num_components == 10 and slic.num_components == 10
+    import json
+    rep = json.loads(slic.slic_model.last_timing_report)
+    assert rep["name"] == "iterate" and len(rep["children"]) == 5
+
+
+def test_single_image_api_parity(port):
+    from fast_slic_b200 import Slic
+    img = make_image("syn", 240, 320, seed=5)
+    s = Slic(num_components=120, min_size_factor=0.1)
+    got = s.iterate(img).view(np.uint16)
+    cl = port.initialize(img, 120)
+    want = port.iterate(img, cl, 10, 10.0, 0.1, 3, True)
+    assert (got == want).all()
+    assert s.slic_model.cluster_array.tobytes() == cl.tobytes()
+    got2 = s.iterate(img).view(np.uint16)  # warm start
+    want2 = port.iterate(img, cl, 10, 10.0, 0.1, 3, True)
+    assert (got2 == want2).all()
