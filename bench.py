@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py -- megapixels/s of the SLIC iterate() hot path (Lab LUT -> 10 x (assign+update) -> full
+assign -> connectivity enforcement) on B200, with the reference's own CPU build timed beside it.
+
+Workload (BASELINE.json configs[1]): 1280x720 RGB, K=1600, compactness=10, 10 iterations,
+subsample_stride=3, convert_to_lab, min_size_factor=0, one step = one batch of
+`--batch` independent images per GPU (default 1 = the "single image" of configs[1]).  Each rank owns its own
+images (weak scaling, no collective on the data path).
+
+  python bench.py --gpus 1 --steps 20 --warmup 5            # this framework
+  python bench.py --impl reference --steps 5 --warmup 1     # the reference's CPU path on the host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: H, W, K, min_size_factor
+    "B": (720, 1280, 1600, 0.0),     # configs[1]
+    "B_msf0.1": (720, 1280, 1600, 0.1),  # configs[4]
+    "C": (1080, 1920, 2000, 0.0),    # configs[2]
+    "D": (2160, 3840, 4000, 0.0),    # configs[3]
+    "A": (480, 640, 200, 0.25),      # configs[0]
+}
+COMPACTNESS, MAX_ITER, STRIDE = 10.0, 10, 3
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="B", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=1, help="images per step per GPU")
+    ap.add_argument("--sigma", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--extra-batched", type=int, default=32,
+                    help="also report throughput at this batch size (0 = skip); informational")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------
+def synth_images_torch(n, H, W, seed, sigma, device):
+    """SURVEY.md section 8(d) synthetic inputs, generated on the device (seeded)."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    y = torch.arange(H, device=device, dtype=torch.float32)[:, None]
+    x = torch.arange(W, device=device, dtype=torch.float32)[None, :]
+    base = torch.stack([torch.sin(x / 37 + y / 91), torch.cos(y / 53 - x / 113), torch.sin((x + y) / 71)], -1)
+    out = torch.empty((n, H, W, 3), dtype=torch.uint8, device=device)
+    for i in range(n):
+        phase = 0.37 * i
+        img = 127 + 100 * torch.roll(base, shifts=(7 * i) % W, dims=1) * (1.0 - 0.1 * np.sin(phase))
+        img = img + torch.randn((H, W, 3), generator=g, device=device) * sigma
+        out[i] = img.clamp(0, 255).to(torch.uint8)
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.lines, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_run(H, W, K, msf, sigma, seconds_budget, n_images=4):
+    """Times the reference's CPU implementation (oracle/_ref = unmodified reference compiled from source;
+    falls back to the plain-C port) on this box's host cores.  Bounded sample, one image at a time
+    (the reference has no batch API)."""
+    from oracle.oracle import Port, Ref, synthetic_image
+    use_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libfslic_ref.so")) or os.path.isdir("/root/reference/src")
+    impl = Ref() if use_ref else Port()
+    cores = os.cpu_count() or 1
+    imgs = [synthetic_image(H, W, 1000 + i, sigma) for i in range(n_images)]
+
+    def one(img, threads):
+        cl = impl.initialize(img, K)
+        t0 = time.perf_counter()
+        if use_ref:
+            impl.iterate(img, cl, MAX_ITER, COMPACTNESS, msf, STRIDE, True, arch="x64/avx2", num_threads=threads)
+        else:
+            impl.iterate(img, cl, MAX_ITER, COMPACTNESS, msf, STRIDE, True)
+        return time.perf_counter() - t0
+
+    one(imgs[0], cores)  # warm-up (OpenMP pool start-up)
+    times, t_start = [], time.perf_counter()
+    while len(times) < 3 or (time.perf_counter() - t_start < seconds_budget and len(times) < 200):
+        times.append(one(imgs[len(times) % n_images], cores))
+    t1 = [one(imgs[i % n_images], 1) for i in range(2)] if use_ref else []
+    mp = H * W / 1e6
+    return {
+        "value": mp / float(np.mean(times)), "best": mp / float(np.min(times)), "unit": "megapixels/s",
+        "cores": cores if use_ref else 1, "kind": "reference" if use_ref else "port",
+        "sample": "%d x iterate() of one %dx%d K=%d image (mean; SlicAvx2 path, %d OpenMP threads), after 1 warm-up"
+                  % (len(times), W, H, K, cores if use_ref else 1),
+        "single_thread_value": (mp / float(np.min(t1))) if t1 else None,
+        "ms_per_image": 1e3 * float(np.mean(times)),
+    }
+
+
+def run_reference_arm(args):
+    H, W, K, msf = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.oracle import Port, Ref, synthetic_image
+    use_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libfslic_ref.so")) or os.path.isdir("/root/reference/src")
+    impl = Ref() if use_ref else Port()
+    cores = os.cpu_count() or 1
+    imgs = [synthetic_image(H, W, 1000 + i, args.sigma) for i in range(4)]
+    per_step = max(1, args.batch)
+
+    def step(i):
+        for b in range(per_step):
+            img = imgs[(i * per_step + b) % len(imgs)]
+            cl = impl.initialize(img, K)
+            if use_ref:
+                impl.iterate(img, cl, MAX_ITER, COMPACTNESS, msf, STRIDE, True, arch="x64/avx2", num_threads=cores)
+            else:
+                impl.iterate(img, cl, MAX_ITER, COMPACTNESS, msf, STRIDE, True)
+
+    for i in range(args.warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(i)
+    dt = time.perf_counter() - t0
+    value = per_step * args.steps * H * W / 1e6 / dt
+    out = {
+        "impl": "reference", "metric": "megapixels/sec (10 iters, K=%d)" % K, "value": value, "unit": "megapixels/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u16 integer",
+        "data": "synthetic",
+        "config": {"workload": "%dx%d RGB, K=%d, compactness=10, 10 iters, stride 3, Lab, min_size_factor=%g, "
+                               "batch=%d image(s)/step (one at a time: the reference has no batch API)" % (W, H, K, msf, per_step)},
+        "cpu_baseline": {"value": value, "unit": "megapixels/s", "cores": cores if use_ref else 1,
+                         "kind": "reference" if use_ref else "port",
+                         "sample": "%d timed steps of %d image(s), SlicAvx2 path of the unmodified reference, %d OpenMP threads"
+                                   % (args.steps, per_step, cores if use_ref else 1)},
+        "e2e": {"value": value, "unit": "megapixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+# ---------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    import torch
+    import torch.distributed as dist
+    from fast_slic_b200 import Slic, get_engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    H, W, K, msf = WORKLOADS[args.workload]
+    B = max(1, args.batch)
+    MP = H * W / 1e6
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- inputs: a pool of distinct images larger than L2 (126 MB) so no step finds its input cached ----
+    img_bytes = H * W * 3
+    pool_steps = max(2, int(np.ceil(300e6 / (img_bytes * B))))
+    pool_steps = min(pool_steps, 128)
+    pool = synth_images_torch(pool_steps * B, H, W, 1000 * (rank + 1), args.sigma, device).view(pool_steps, B, H, W, 3)
+    eng = get_engine(H, W, K, max(B, args.extra_batched if args.extra_batched > 0 else 1), local_rank)
+    pristine = eng.initialize_clusters(pool[0])           # centres are image independent; colours get re-seeded
+    clusters = pristine.clone()
+    labels = torch.empty((B, H, W), dtype=torch.int16, device=device)
+    p_fast = eng.params(COMPACTNESS, msf, STRIDE, True, MAX_ITER, collect_timing=0)
+    p_prof = eng.params(COMPACTNESS, msf, STRIDE, True, MAX_ITER, collect_timing=2)
+
+    def step(i, params):
+        clusters.copy_(pristine)                           # every step is a cold start, like a fresh Slic()
+        eng.iterate(pool[i % pool_steps], clusters, params, labels)
+
+    # ---- kernel-resident throughput: inputs already in HBM ----
+    for i in range(args.warmup):
+        step(i, p_fast)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(args.warmup + i, p_fast)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if sampler else None
+    launches = eng.launches_last_iterate() * args.steps
+    value = world * B * args.steps * MP / (ms / 1e3)
+
+    # ---- roofline of the dominant kernel: per-launch CUDA events on the launch stream, same workload ----
+    k_ms, k_n = 0.0, 0
+    for i in range(max(3, min(args.steps, 10))):
+        step(i, p_prof)
+        a, n = eng.assign_kernel_time()
+        k_ms += a
+        k_n += n
+    stage = eng.stage_ms()
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    if os.path.exists(peaks_path):
+        try:
+            peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "MEASURED_PEAKS.json hbm_gbs"
+        except Exception:
+            pass
+    sub_px = B * W * ((H + STRIDE - 1) // STRIDE)          # pixels one subsampled launch touches (rem = 0 rows)
+    alg_bytes = 6.0 * sub_px                               # 4 B quad read + 2 B label written per pixel
+    avg_ms = k_ms / max(k_n, 1)
+    achieved = alg_bytes / (avg_ms * 1e-3) / 1e9 if k_n else 0.0
+    roofline = {"kernel": "k_assign_tiles<4,true> (fused assign+update, subsampled pass)", "bound": "hbm",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "bytes_per_launch": alg_bytes, "avg_launch_us": avg_ms * 1e3,
+                "launches_timed": k_n, "stage_ms_last_step": stage}
+
+    # ---- end to end through the public API with HOST buffers (H2D + compute + D2H inside the timed region) ----
+    slic = Slic(num_components=K, compactness=COMPACTNESS, min_size_factor=msf, subsample_stride=STRIDE)
+    slic.slic_model.device = local_rank
+    n_host = min(pool_steps, 8)
+    host_imgs = torch.empty((n_host, B, H, W, 3), dtype=torch.uint8).pin_memory()
+    host_imgs.copy_(pool[:n_host])
+    host_np = host_imgs.numpy()
+    host_pristine = torch.empty(pristine.shape, dtype=torch.uint8).pin_memory()
+    host_pristine.copy_(pristine)
+    from fast_slic_b200 import CLUSTER_DTYPE
+    cl_np = host_pristine.numpy().view(CLUSTER_DTYPE).reshape(B, K)
+    work_cl = torch.empty(pristine.shape, dtype=torch.uint8).pin_memory().numpy().view(CLUSTER_DTYPE).reshape(B, K)
+    lab_np = torch.empty((B, H, W), dtype=torch.int16).pin_memory().numpy()
+
+    def e2e_step(i):
+        work_cl[...] = cl_np
+        slic.iterate_batch(host_np[i % n_host], max_iter=MAX_ITER, clusters=work_cl)
+
+    # iterate_batch allocates its own label array; for a tight loop use the engine's host entry directly
+    def e2e_step_tight(i):
+        work_cl[...] = cl_np
+        eng.iterate_host(host_np[i % n_host], work_cl, p_fast, lab_np)
+
+    e2e_step(0)
+    for i in range(args.warmup):
+        e2e_step_tight(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_step_tight(i)
+    torch.cuda.synchronize()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_value = world * B * args.steps * MP / dt
+    h2d = B * (H * W * 3 + K * 32)
+    d2h = B * (H * W * 2 + K * 32)
+
+    # ---- informational: batched throughput on the same image shape ----
+    batched = None
+    if args.extra_batched > 0 and args.extra_batched != B:
+        EB = args.extra_batched
+        nsteps_b = max(2, pool_steps * B // EB)
+        flat = pool.view(-1, H, W, 3)
+        nb = flat.shape[0] // EB
+        if nb >= 1:
+            pr = eng.initialize_clusters(flat[:EB])
+            cb = pr.clone()
+            lb = torch.empty((EB, H, W), dtype=torch.int16, device=device)
+            for i in range(2):
+                cb.copy_(pr); eng.iterate(flat[(i % nb) * EB:(i % nb + 1) * EB], cb, p_fast, lb)
+            barrier()
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0.record()
+            for i in range(nsteps_b):
+                cb.copy_(pr); eng.iterate(flat[(i % nb) * EB:(i % nb + 1) * EB], cb, p_fast, lb)
+            b1.record()
+            barrier()
+            bms = max_over_ranks(b0.elapsed_time(b1))
+            kb_ms, kb_n = 0.0, 0
+            for i in range(3):
+                cb.copy_(pr); eng.iterate(flat[(i % nb) * EB:(i % nb + 1) * EB], cb, p_prof, lb)
+                a, n = eng.assign_kernel_time(); kb_ms += a; kb_n += n
+            ach = 6.0 * EB * W * ((H + STRIDE - 1) // STRIDE) / (kb_ms / max(kb_n, 1) * 1e-3) / 1e9
+            batched = {"batch": EB, "value": world * EB * nsteps_b * MP / (bms / 1e3), "unit": "megapixels/s",
+                       "ms_per_step": bms / nsteps_b, "assign_kernel_GBps": ach, "assign_kernel_frac": ach / peak,
+                       "stage_ms": eng.stage_ms()}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference_run(H, W, K, msf, args.sigma, seconds_budget=12.0)
+
+    if rank == 0:
+        out = {
+            "metric": "megapixels/sec (10 iters, K=%d)" % K, "value": value, "unit": "megapixels/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u16 integer",
+            "data": "synthetic",
+            "config": {"workload": "%dx%d RGB, K=%d, compactness=10, 10 iters, stride 3, Lab, min_size_factor=%g, "
+                                   "batch=%d image(s)/step/GPU (BASELINE configs[1])" % (W, H, K, msf, B),
+                       "l2": "inputs rotate through a %d MB pool of distinct images (> 126 MB L2)"
+                             % (pool_steps * B * img_bytes // 1000000),
+                       "parallelism": "independent images per rank, no data-path collective"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "megapixels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * dt / args.steps,
+                    "api": "fslic_b200_iterate_host via fast_slic_b200.Engine.iterate_host (pinned host buffers)"},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "batched": batched,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -160,7 +160,7 @@ class SlicModel(object):
         H, W, _ = image.shape
         eng = get_engine(H, W, self._num_components, 1, self.device)
         params = eng.params(compactness, min_size_factor, subsample_stride, self.convert_to_lab, max_iter,
-                            collect_timing=True)
+                            collect_timing=1)
         clusters = np.ascontiguousarray(self._clusters)[None]
         labels = eng.iterate_host(image[None], clusters, params)
         self._clusters = clusters[0]

@@ -65,6 +65,12 @@ struct fslic_ctx {
     float stage_ms[FSLIC_T_COUNT] = {0, 0, 0, 0, 0, 0};
     int last_launches = 0;
     int max_smem_optin = 0;
+    // per-launch timing of the dominant kernel (k_assign_tiles on the subsampled passes)
+    std::vector<cudaEvent_t> kev;
+    int kev_used = 0;
+    bool kev_on = false;
+    float assign_kernel_ms = 0.f;
+    int assign_kernel_launches = 0;
 };
 
 extern "C" const char* fslic_b200_last_error(void) { return g_err.c_str(); }
@@ -115,6 +121,7 @@ extern "C" int fslic_b200_destroy(fslic_ctx* c) {
     if (c->h_lab) cudaFreeHost(c->h_lab);
     for (auto& e : c->ev)
         if (e) cudaEventDestroy(e);
+    for (auto& e : c->kev) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
     return FSLIC_OK;
@@ -352,12 +359,24 @@ static int run_assign_pass(fslic_ctx* c, int batch, int stride, int rem, int cfg
         if (occ < 1) occ = 1;
         long grid = (long)c->num_sms * occ;
         if (grid > total) grid = total;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (c->kev_on && update) {
+            while ((int)c->kev.size() < c->kev_used + 2) {
+                cudaEvent_t e;
+                CK(cudaEventCreate(&e));
+                c->kev.push_back(e);
+            }
+            e0 = c->kev[c->kev_used++];
+            e1 = c->kev[c->kev_used++];
+            CK(cudaEventRecord(e0, st));
+        }
         if (update)
             k_assign_tiles<4, true><<<(int)grid, AS_THREADS, g.smem, st>>>(ap, c->quad, c->labels, c->cinfo, c->cell_start,
                                                                            c->cell_items, c->acc, c->sptable, c->overflow);
         else
             k_assign_tiles<4, false><<<(int)grid, AS_THREADS, g.smem, st>>>(ap, c->quad, c->labels, c->cinfo, c->cell_start,
                                                                             c->cell_items, c->acc, c->sptable, c->overflow);
+        if (e1) CK(cudaEventRecord(e1, st));
         // overflowed tiles (normally none): generic kernel over the recorded list, grid sized for a modest count
         int og = (int)(total < 4096 ? total : 4096);
         if (update)
@@ -413,6 +432,8 @@ extern "C" int fslic_b200_iterate(fslic_ctx* c, const uint8_t* d_images, fslic_c
     if (S == 0) coef = 0.f;  // 1/(0/compactness) = inf in the reference; with S == 0 only m = 0 is ever used -> inf*0 = NaN -> (u16) UB; use 0
     int launches = 0;
     const bool timing = p->collect_timing != 0;
+    c->kev_on = p->collect_timing >= 2;
+    c->kev_used = 0;
     if (timing) CK(cudaEventRecord(c->ev[0], st));
     rc = launch_lab(c, d_images, c->quad, batch, p->convert_to_lab, st);
     if (rc) return rc;
@@ -446,8 +467,22 @@ extern "C" int fslic_b200_iterate(fslic_ctx* c, const uint8_t* d_images, fslic_c
         CK(cudaEventElapsedTime(&ms, c->ev[2], c->ev[3])); c->stage_ms[FSLIC_T_FULL_ASSIGN] = ms;
         CK(cudaEventElapsedTime(&ms, c->ev[3], c->ev[4])); c->stage_ms[FSLIC_T_CCA] = ms;
         CK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[4])); c->stage_ms[FSLIC_T_TOTAL] = ms;
+        c->assign_kernel_ms = 0.f;
+        c->assign_kernel_launches = 0;
+        for (int i = 0; i + 1 < c->kev_used; i += 2) {
+            CK(cudaEventElapsedTime(&ms, c->kev[i], c->kev[i + 1]));
+            c->assign_kernel_ms += ms;
+            c->assign_kernel_launches++;
+        }
     }
     c->last_launches = launches;
+    return FSLIC_OK;
+}
+
+extern "C" int fslic_b200_assign_kernel_time(fslic_ctx* c, float* total_ms, int* launches) {
+    if (!c || !total_ms || !launches) return set_err(FSLIC_EINVAL, "NULL argument");
+    *total_ms = c->assign_kernel_ms;
+    *launches = c->assign_kernel_launches;
     return FSLIC_OK;
 }
 

@@ -65,9 +65,9 @@ class Engine:
 
     @staticmethod
     def params(compactness=10.0, min_size_factor=0.25, subsample_stride=3, convert_to_lab=True, max_iter=10,
-               collect_timing=False):
+               collect_timing=0):
         return Params(float(compactness), float(min_size_factor), int(subsample_stride), int(bool(convert_to_lab)),
-                      int(max_iter), int(bool(collect_timing)))
+                      int(max_iter), int(collect_timing))
 
     # -- device entry points -------------------------------------------------------------------
     def initialize_clusters(self, images, clusters=None):
@@ -137,6 +137,12 @@ class Engine:
         out = (C.c_float * 6)()
         check(self._L.fslic_b200_stage_ms(self._h, out, 6))
         return dict(zip(_lib.STAGE_NAMES, [float(v) for v in out]))
+
+    def assign_kernel_time(self):
+        """(total ms, launches) of the fused assign+update kernel in the last iterate (collect_timing=2)."""
+        ms, n = C.c_float(), C.c_int()
+        check(self._L.fslic_b200_assign_kernel_time(self._h, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
 
     def launches_last_iterate(self):
         return int(self._L.fslic_b200_launches_last_iterate(self._h))

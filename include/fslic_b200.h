@@ -42,7 +42,7 @@ typedef struct fslic_params {
     int32_t subsample_stride;/* context.h:26 (subsample_stride_config) */
     int32_t convert_to_lab;  /* context.h:30 */
     int32_t max_iter;        /* argument of iterate(), context.h:72 */
-    int32_t collect_timing;  /* !=0: record per-stage CUDA-event timings (fstimer analogue, timer.cpp:4-49) */
+    int32_t collect_timing;  /* 1: per-stage CUDA-event timings (fstimer analogue, timer.cpp:4-49); 2: + per-launch assign kernel */
 } fslic_params;
 
 enum {
@@ -110,6 +110,10 @@ int fslic_b200_rgb_to_quad(fslic_ctx* ctx, const uint8_t* d_images, uint8_t* d_q
  * differential tests: d_area int32[n]; writes d_kept u8[n] (1 = in the selected top-`middle`). */
 int fslic_b200_debug_heap_select(fslic_ctx* ctx, const int32_t* d_area, int n, int middle, uint8_t* d_kept,
                                  void* stream);
+
+/* With collect_timing >= 2: summed device time (CUDA events on the launch stream) and launch count of the
+ * dominant kernel -- the fused assign+update kernel on the subsampled passes -- in the last iterate(). */
+int fslic_b200_assign_kernel_time(fslic_ctx* ctx, float* total_ms, int* launches);
 
 /* Milliseconds spent per stage in the last iterate() with collect_timing != 0. */
 int fslic_b200_stage_ms(fslic_ctx* ctx, float* out_ms, int count);
