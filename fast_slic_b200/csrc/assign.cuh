@@ -20,8 +20,8 @@
 //   2. first pass only: re-seed the cluster colour from the quad image (context.cpp:128-135);
 //   3. clamp centres into the image (context.cpp:209-212), truncate to int16 (context.cpp:266-267),
 //      derive the visiting-order key, write the 16-byte CInfo record;
-//   4. counting-sort the clusters into a uniform cell grid of pitch G >= S, so a tile can collect
-//      the clusters whose window may touch it from a few contiguous ranges.
+//   4. counting-sort the CInfo records into a uniform cell grid of pitch G >= S, so a tile can collect
+//      the clusters whose window may touch it from a few contiguous ranges of the sorted array.
 // ---------------------------------------------------------------------------------------------
 struct PrepParams {
     int H, W, K, S, T;
@@ -32,18 +32,19 @@ struct PrepParams {
 };
 
 __global__ void __launch_bounds__(1024) k_prepare(PrepParams pp, fslic_cluster* __restrict__ clusters,
-                                                   uint32_t* __restrict__ acc, const uint32_t* __restrict__ quad,
-                                                   CInfo* __restrict__ cinfo, int* __restrict__ cell_start,
-                                                   int* __restrict__ cell_items) {
+                                                   unsigned long long* __restrict__ acc,
+                                                   const uint32_t* __restrict__ quad, CInfo* __restrict__ cinfo,
+                                                   int* __restrict__ cell_start,
+                                                   CInfo* __restrict__ cinfo_tmp) {
     extern __shared__ int s_cnt[];  // ncell + 1 counters, then 1024/32 warp sums
     const int b = blockIdx.x;
     const int tid = threadIdx.x, nt = blockDim.x;
     fslic_cluster* cl = clusters + (size_t)b * pp.K;
-    uint32_t* ac = acc + (size_t)b * pp.K * 6;
+    unsigned long long* ac = acc + (size_t)b * pp.K * 4;
     const uint32_t* qd = quad + (size_t)b * pp.H * pp.W;
-    CInfo* ci = cinfo + (size_t)b * pp.K;
+    CInfo* ci = cinfo_tmp + (size_t)b * pp.K;          // by cluster index (scratch)
+    CInfo* ci_sorted = cinfo + (size_t)b * pp.K;       // by cell, what the assign kernels read
     int* cs = cell_start + (size_t)b * (pp.ncell + 1);
-    int* items = cell_items + (size_t)b * pp.K;
 
     for (int c = tid; c <= pp.ncell; c += nt) s_cnt[c] = 0;
     __syncthreads();
@@ -51,18 +52,19 @@ __global__ void __launch_bounds__(1024) k_prepare(PrepParams pp, fslic_cluster* 
     for (int k = tid; k < pp.K; k += nt) {
         fslic_cluster c = cl[k];
         if (pp.finalize) {
-            const uint32_t n = ac[k * 6 + 0];
+            // packed sums: [0] = n | sum_y << 32, [1] = sum_x | sum_L << 32, [2] = sum_a | sum_b << 32
+            const unsigned long long w0 = ac[k * 4 + 0], w1 = ac[k * 4 + 1], w2 = ac[k * 4 + 2];
+            const uint32_t n = (uint32_t)w0;
             c.num_members = n;  // written even when n == 0 (context.cpp:360-362)
             if (n > 0) {
                 const int32_t in = (int32_t)n, half = in / 2;
-                c.y = (float)(((int32_t)ac[k * 6 + 1] + half) / in);
-                c.x = (float)(((int32_t)ac[k * 6 + 2] + half) / in);
-                c.r = (float)(((int32_t)ac[k * 6 + 3] + half) / in);
-                c.g = (float)(((int32_t)ac[k * 6 + 4] + half) / in);
-                c.b = (float)(((int32_t)ac[k * 6 + 5] + half) / in);
+                c.y = (float)(((int32_t)(w0 >> 32) + half) / in);
+                c.x = (float)(((int32_t)(uint32_t)w1 + half) / in);
+                c.r = (float)(((int32_t)(w1 >> 32) + half) / in);
+                c.g = (float)(((int32_t)(uint32_t)w2 + half) / in);
+                c.b = (float)(((int32_t)(w2 >> 32) + half) / in);
             }
-#pragma unroll
-            for (int f = 0; f < 6; f++) ac[k * 6 + f] = 0;
+            ac[k * 4 + 0] = 0; ac[k * 4 + 1] = 0; ac[k * 4 + 2] = 0;
         }
         if (pp.first) {
             int y = min(max((int)c.y, 0), pp.H - 1), x = min(max((int)c.x, 0), pp.W - 1);
@@ -129,11 +131,11 @@ __global__ void __launch_bounds__(1024) k_prepare(PrepParams pp, fslic_cluster* 
         __syncthreads();
     }
     for (int k = tid; k < pp.K; k += nt) {
-        const int32_t cyx = ci[k].cyx;
-        const int cy = (int16_t)(cyx & 0xffff), cx = cyx >> 16;
+        const CInfo r = ci[k];
+        const int cy = (int16_t)(r.cyx & 0xffff), cx = r.cyx >> 16;
         const int cell = (cy / pp.G) * pp.cellW + (cx / pp.G);
         const int slot = atomicAdd(&s_cnt[cell], 1);
-        items[slot] = k;
+        ci_sorted[slot] = r;  // order inside a cell is arbitrary: consumers rank by sortkey
     }
 }
 
@@ -163,304 +165,382 @@ struct AssignParams {
     int cfg_stride;    // the configured subsample stride (freshness test)
     int fresh_from;    // rows with (i % cfg_stride) >= fresh_from were never assigned before
     int G, cellW, cellH, ncell;
+    uint32_t Ginv;     // ceil(2^32 / G): x / G == __umulhi(x, Ginv) for 0 <= x < 65536 (x * G < 2^32)
     int OY, OX, TS, tbl_elems;
-    int tiles_x, tiles_y, ntiles;  // per image
+    int tiles_x, tiles_y, ntiles;  // warp tiles (32 columns x R sub-rows) per image
     float coef;        // generic path only
 };
 
 #define AS_WARPS 16
 #define AS_THREADS (AS_WARPS * 32)
-#define AS_WX 4            // warps across  -> tile is 128 columns
-#define AS_WY 4            // warps down
-#define AS_NC 256          // candidate capacity of a tile; beyond it the tile goes to the generic kernel
+#define AS_LIST 32  // candidate capacity of one warp tile; beyond it the tile takes the brute-force path
+
+__device__ __forceinline__ int div_g(int x, uint32_t ginv) { return (int)__umulhi((uint32_t)x, ginv); }
+
+// Packed per-cluster accumulators, 3 x u64 (+1 pad) so one update is 3 RED.64 instead of 6 RED.32:
+//   [0] = n | sum_y << 32      [1] = sum_x | sum_L << 32      [2] = sum_a | sum_b << 32
+// Every half stays far below 2^32 (sum_y <= n*H), so the halves never carry into each other.
+__device__ __forceinline__ void acc_add_pixel(unsigned long long* ac, uint32_t label, int i, int j, uint32_t q) {
+    atomicAdd(&ac[label * 4 + 0], 1ull | ((unsigned long long)(uint32_t)i << 32));
+    atomicAdd(&ac[label * 4 + 1], (unsigned long long)(uint32_t)j | ((unsigned long long)(q & 0xff) << 32));
+    atomicAdd(&ac[label * 4 + 2], (unsigned long long)((q >> 8) & 0xff) | ((unsigned long long)((q >> 16) & 0xff) << 32));
+}
+
+// Brute-force assignment of one pixel straight from the cell grid: lexicographic minimum of
+// (d, phase, k) over the clusters whose window covers (i, j).  Returns the new label (or the kept
+// one) and stores it.  Used by the generic kernel and by warp tiles whose candidate list overflowed.
+__device__ __forceinline__ uint32_t assign_pixel_generic(const AssignParams& ap, int i, int j, uint32_t q,
+                                                          const CInfo* __restrict__ ci, const int* __restrict__ cs,
+                                                          uint16_t* __restrict__ lb) {
+    const int S = ap.S, W = ap.W, H = ap.H;
+    unsigned long long best = ~0ull;
+    const int cr0 = max(i - S, 0) / ap.G, cr1 = min(i + S, H - 1) / ap.G;
+    const int cc0 = max(j - S, 0) / ap.G, cc1 = min(j + S, W - 1) / ap.G;
+    for (int cr = cr0; cr <= cr1; cr++) {
+        const int s = cs[cr * ap.cellW + cc0], e = cs[cr * ap.cellW + cc1 + 1];
+        for (int u = s; u < e; u++) {
+            const CInfo r = ci[u];
+            const int cy = (int16_t)(r.cyx & 0xffff), cx = r.cyx >> 16;
+            const int di = abs(i - cy), dj = abs(j - cx);
+            if (di > S || dj > S) continue;
+            const uint32_t sp = (uint16_t)__float2uint_rz(__fmul_rn(ap.coef, (float)(di + dj)));
+            const uint32_t d = sad4_acc(q, r.color, sp) & 0xffffu;  // u16 arithmetic like the scalar reference
+            const unsigned long long key = ((unsigned long long)d << 32) | r.sortkey;
+            best = key < best ? key : best;
+        }
+    }
+    uint32_t label;
+    if (best != ~0ull && (uint32_t)(best >> 32) < 0xFFFFu) {
+        label = (uint32_t)(best & 0xffff);
+        lb[(size_t)i * W + j] = (uint16_t)label;
+    } else if ((i % ap.cfg_stride) >= ap.fresh_from) {
+        lb[(size_t)i * W + j] = 0xFFFF;
+        label = 0xFFFF;
+    } else {
+        label = lb[(size_t)i * W + j];  // keep the label of an earlier pass (context.cpp:289-294 never fires)
+    }
+    return label;
+}
+
+__device__ __forceinline__ uint32_t lds_u16(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+
+// exact per-byte equality -> 0x80 in every byte of w that equals the corresponding byte of m
+__device__ __forceinline__ uint32_t eq80(uint32_t w, uint32_t m) {
+    const uint32_t t = w ^ m;
+    const uint32_t a = (t & 0x7f7f7f7fu) + 0x7f7f7f7fu;
+    return ~(a | t) & 0x80808080u;
+}
+
+__device__ __forceinline__ void mma_u8_16x8x32(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                               uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
 
 // ---------------------------------------------------------------------------------------------
-// k_assign_tiles<R, UPDATE>: persistent CTAs; each loops over tiles of 128 columns x (4*R) sub-rows.
-//   per tile : collect the clusters whose window can touch the tile from the cell grid, sort them
-//              by (phase, k) (rank-by-counting), keep them in shared memory;
-//   per warp : 32 columns x R sub-rows; ballot-filter the tile list down to the clusters that can
-//              touch the warp's footprint (order preserved);
-//   per pixel and candidate:  LDS.U16 patch entry -> VABSDIFF4.U8.ACC (colour SAD + spatial) ->
-//              IMAD (d << 16 | rank) -> VIMNMX;
-//   update   : warp-aggregated (ballot + REDUX) sums into per-tile shared accumulators, flushed with
-//              one RED per touched (cluster, field) -- exact, integer sums are order independent.
+// k_assign_warp<TS, STRIDE, UPDATE>: the hot kernel.  Persistent CTAs (the spatial patch is loaded
+// into shared memory once per CTA); inside a CTA every WARP is autonomous -- no block barrier
+// after the patch load.  A warp walks "super tiles" of 4 horizontally adjacent warp tiles
+// (each 32 columns x 4 sub-rows):
+//   L. candidate lists for the 4 tiles at once, 8 lanes per tile: the clusters whose (2S+1)^2
+//      window can touch the tile are collected from the cell grid (exact filter, ballot
+//      compaction, <= 32 per tile), ranked by (phase, k) -- the reference's visiting order
+//      (context.cpp:214-242) -- and staged {colour, patch offset} by rank in per-warp shared memory;
+//   then per tile:
+//   1. 4 quad loads per lane (LDG.32, 128 B per warp row);
+//   2. per candidate and pixel:  LDS.U16 patch entry [immediate row offsets: TS and STRIDE are
+//      compile-time] -> VABSDIFF4.U8.ACC (colour SAD + spatial) -> IMAD (d << 16 | rank) -> VIMNMX;
+//   3. labels out (STG.U16, 64 B per warp row);
+//   4. update sums (context.cpp:316-327) as an exact int8 tensor-core product
+//        [1, row, lane, L, a, b]^T (features x pixels)  x  one-hot(rank) (pixels x candidates)
+//      (mma.sync m16n8k32 u8 x u8 -> s32, 4 MMAs per 128 pixels and 8 candidates), then 3 RED.64
+//      per cluster that received pixels.  Integer sums are order independent => exact.
 // HBM per processed pixel: 4 B quad read + 2 B label written.
 // ---------------------------------------------------------------------------------------------
-template <int R, bool UPDATE>
-__global__ void __launch_bounds__(AS_THREADS) k_assign_tiles(AssignParams ap, const uint32_t* __restrict__ quad,
-                                                              uint16_t* __restrict__ labels,
-                                                              const CInfo* __restrict__ cinfo,
-                                                              const int* __restrict__ cell_start,
-                                                              const int* __restrict__ cell_items,
-                                                              uint32_t* __restrict__ acc,
-                                                              const uint16_t* __restrict__ g_tbl,
-                                                              int* __restrict__ overflow_list) {
+#define AS_R 4   // sub-rows per lane
+#define AS_T 4   // warp tiles per super tile
+#define AS_STAGE_BYTES (AS_WARPS * AS_T * AS_LIST * 22)
+
+template <int TS, int STRIDE, bool UPDATE>
+__global__ void __launch_bounds__(AS_THREADS, 2) k_assign_warp(AssignParams ap, const uint32_t* __restrict__ quad,
+                                                               uint16_t* __restrict__ labels,
+                                                               const CInfo* __restrict__ cinfo,
+                                                               const int* __restrict__ cell_start,
+                                                               unsigned long long* __restrict__ acc,
+                                                               const uint16_t* __restrict__ g_tbl) {
+    constexpr int R = AS_R;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint16_t* s_tbl = reinterpret_cast<uint16_t*>(smem_raw);
-    __shared__ uint2 s_ent[AS_NC];      // sorted: {colour, patch base offset (u16 elements)}
-    __shared__ int32_t s_cyx[AS_NC];    // sorted: packed centre, for the warp filter
-    __shared__ uint16_t s_k[AS_NC];     // sorted: cluster index
-    __shared__ uint32_t s_ukey[AS_NC];  // unsorted gather
-    __shared__ uint32_t s_ucol[AS_NC];
-    __shared__ int32_t s_ucyx[AS_NC];
-    __shared__ uint32_t s_acc[UPDATE ? AS_NC * 6 : 1];
-    __shared__ int s_n;
-
+    // per-warp private staging block behind the patch in dynamic shared memory (AS_STAGE_BYTES in total):
+    //   [ent: AS_T x 32 x uint2][ukey: AS_T x 32 x u32][ucol: same][ucyx: same][k: AS_T x 32 x u16]
+    // the MMA A staging [32 pixel lanes][8 features] x u32 aliases ukey+ucol of the SAME warp (dead once ranked)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wx = warp % AS_WX, wy = warp / AS_WX;
+    unsigned char* wst = smem_raw + ((ap.tbl_elems * 2 + 15) & ~15) + warp * (AS_T * AS_LIST * 22);
+    uint2 (*s_ent)[AS_LIST] = reinterpret_cast<uint2 (*)[AS_LIST]>(wst);
+    uint32_t (*s_ukey)[AS_LIST] = reinterpret_cast<uint32_t (*)[AS_LIST]>(wst + AS_T * AS_LIST * 8);
+    uint32_t (*s_ucol)[AS_LIST] = reinterpret_cast<uint32_t (*)[AS_LIST]>(wst + AS_T * AS_LIST * 12);
+    int32_t (*s_ucyx)[AS_LIST] = reinterpret_cast<int32_t (*)[AS_LIST]>(wst + AS_T * AS_LIST * 16);
+    uint16_t (*s_k)[AS_LIST] = reinterpret_cast<uint16_t (*)[AS_LIST]>(wst + AS_T * AS_LIST * 20);
+    uint32_t (*s_feat)[8] = reinterpret_cast<uint32_t (*)[8]>(wst + AS_T * AS_LIST * 8);
+    static_assert(32 * 8 * 4 <= AS_T * AS_LIST * 8, "the MMA staging must fit in ukey + ucol");
 
-    // the patch is loaded once per CTA and reused for every tile this CTA processes
     for (int t = tid; t < (ap.tbl_elems + 1) / 2; t += AS_THREADS)
         reinterpret_cast<uint32_t*>(s_tbl)[t] = reinterpret_cast<const uint32_t*>(g_tbl)[t];
+    __syncthreads();
 
     const int S = ap.S, W = ap.W, H = ap.H;
-    const long total_tiles = (long)ap.ntiles * ap.B;
-    for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int b = (int)(tile / ap.ntiles);
-        const int tl = (int)(tile - (long)b * ap.ntiles);
-        const int ty = tl / ap.tiles_x, tx = tl - ty * ap.tiles_x;
-        const int tj0 = tx * (AS_WX * 32);
-        const int tsr0 = ty * (AS_WY * R);
-        const int tsr1 = min(tsr0 + AS_WY * R, ap.nsub) - 1;  // last valid sub-row of the tile
-        const int ti0 = ap.rem + tsr0 * ap.stride, ti1 = ap.rem + tsr1 * ap.stride;
-        const int tj1 = min(tj0 + AS_WX * 32, W) - 1;
+    const int stride = STRIDE ? STRIDE : ap.stride;
+    const int g = lane >> 2, tig = lane & 3;   // MMA fragment coordinates
+    const int grp = lane >> 3, gl = lane & 7;  // list building: 8 lanes per tile
+    const int rowpix = stride * W;
 
+    // super-tile walk without divisions: (b, ty, sx) advance by a fixed (db, dty, dsx) with carries
+    const int stx = (ap.tiles_x + AS_T - 1) / AS_T;  // super tiles per tile row
+    const long per_img = (long)stx * ap.tiles_y;
+    const long total = per_img * ap.B;
+    const long wstride = (long)gridDim.x * AS_WARPS;
+    const long first = (long)blockIdx.x * AS_WARPS + warp;
+    int b = (int)(first / per_img);
+    const int tl0 = (int)(first - (long)b * per_img);
+    int ty = tl0 / stx, sx = tl0 - ty * stx;
+    const int db = (int)(wstride / per_img);
+    const int dtl = (int)(wstride - (long)db * per_img);
+    const int dty = dtl / stx, dsx = dtl - dty * stx;
+    for (long st = first; st < total; st += wstride, b += db, ty += dty, sx += dsx) {
+        if (sx >= stx) { sx -= stx; ty += 1; }
+        if (ty >= ap.tiles_y) { ty -= ap.tiles_y; b += 1; }
+        const int wsr0 = ty * R;
+        const int nrow = min(R, ap.nsub - wsr0);  // valid sub-rows of this tile row (>= 1)
+        const int wi0 = ap.rem + wsr0 * stride, wi1 = wi0 + (nrow - 1) * stride;
+        const size_t img_off = (size_t)b * H * W;
         const CInfo* ci = cinfo + (size_t)b * ap.K;
         const int* cs = cell_start + (size_t)b * (ap.ncell + 1);
-        const int* items = cell_items + (size_t)b * ap.K;
+        unsigned long long* ac = acc + (size_t)b * ap.K * 4;
 
-        __syncthreads();  // previous tile fully consumed (also orders the table load on the first pass)
-        if (tid == 0) s_n = 0;
-        if (UPDATE)
-            for (int t = tid; t < AS_NC * 6; t += AS_THREADS) s_acc[t] = 0;
-        __syncthreads();
-
-        // ---- gather: clusters with cy in [ti0-S, ti1+S], cx in [tj0-S, tj1+S] ----
+        // ---- L. candidate lists of the 4 tiles, 8 lanes each ----
+        // tile of this lane group: columns [gj0, gj0+31]; wanted clusters: cy in [wi0-S, wi1+S], cx in [gj0-S, gj0+31+S]
+        const int gtx = sx * AS_T + grp;
+        const bool gvalid = gtx < ap.tiles_x;
+        const int gj0 = gtx * 32;
+        int n_g = 0;  // candidates found for this group's tile (same value in its 8 lanes)
         {
-            const int cr0 = max(ti0 - S, 0) / ap.G, cr1 = min(ti1 + S, H - 1) / ap.G;
-            const int cc0 = max(tj0 - S, 0) / ap.G, cc1 = min(tj1 + S, W - 1) / ap.G;
-            for (int cr = cr0 + warp; cr <= cr1; cr += AS_WARPS) {
-                const int s = cs[cr * ap.cellW + cc0], e = cs[cr * ap.cellW + cc1 + 1];
-                for (int t = s + lane; t < e; t += 32) {
-                    const int k = items[t];
-                    const CInfo r = ci[k];
-                    const int cy = (int16_t)(r.cyx & 0xffff), cx = r.cyx >> 16;
-                    if (cy >= ti0 - S && cy <= ti1 + S && cx >= tj0 - S && cx <= tj1 + S) {
-                        const int slot = atomicAdd(&s_n, 1);
-                        if (slot < AS_NC) {
-                            s_ukey[slot] = r.sortkey;
-                            s_ucol[slot] = r.color;
-                            s_ucyx[slot] = r.cyx;
-                        }
+            const int cr0 = div_g(max(wi0 - S, 0), ap.Ginv), cr1 = div_g(min(wi1 + S, H - 1), ap.Ginv);
+            const int cc0 = div_g(max(gj0 - S, 0), ap.Ginv), cc1 = div_g(min(gj0 + 31 + S, W - 1), ap.Ginv);
+            for (int crb = cr0; crb <= cr1; crb += 8) {
+                const int cr = crb + gl;
+                int rs = 0, cnt = 0;
+                if (gvalid && cr <= cr1) {
+                    rs = cs[cr * ap.cellW + cc0];
+                    cnt = cs[cr * ap.cellW + cc1 + 1] - rs;
+                }
+                int incl = cnt;  // inclusive scan inside the 8-lane group
+#pragma unroll
+                for (int o = 1; o < 8; o <<= 1) {
+                    const int y = __shfl_up_sync(FSLIC_FULL, incl, o, 8);
+                    if (gl >= o) incl += y;
+                }
+                const int T = __shfl_sync(FSLIC_FULL, incl, 7, 8);
+                const int Tmax = __reduce_max_sync(FSLIC_FULL, T);
+                for (int t0 = 0; t0 < Tmax; t0 += 8) {
+                    const int t = t0 + gl;
+                    int row = 0;
+#pragma unroll
+                    for (int r = 0; r < 7; r++) row += (t >= __shfl_sync(FSLIC_FULL, incl, r, 8));
+                    const int rincl = __shfl_sync(FSLIC_FULL, incl, row, 8);
+                    const int rcnt = __shfl_sync(FSLIC_FULL, cnt, row, 8);
+                    const int rstart = __shfl_sync(FSLIC_FULL, rs, row, 8);
+                    bool hit = false;
+                    CInfo r;
+                    if (t < T) {
+                        r = ci[rstart + (t - (rincl - rcnt))];
+                        const int cy = (int16_t)(r.cyx & 0xffff), cx = r.cyx >> 16;
+                        hit = (cy >= wi0 - S) && (cy <= wi1 + S) && (cx >= gj0 - S) && (cx <= gj0 + 31 + S);
                     }
+                    const unsigned gb = (__ballot_sync(FSLIC_FULL, hit) >> (grp * 8)) & 0xffu;
+                    const int slot = n_g + __popc(gb & ((1u << gl) - 1));
+                    if (hit && slot < AS_LIST) {
+                        s_ukey[grp][slot] = r.sortkey;
+                        s_ucol[grp][slot] = r.color;
+                        s_ucyx[grp][slot] = r.cyx;
+                    }
+                    n_g += __popc(gb);
                 }
             }
         }
-        __syncthreads();
-        const int n = s_n;
-        if (n > AS_NC) {  // too many clusters around this tile: defer to the generic kernel
-            if (tid == 0) {
-                const int slot = atomicAdd(&overflow_list[0], 1);
-                overflow_list[1 + slot] = (int)tile;
+        __syncwarp();
+        {   // rank by (phase, k) (keys are unique) and stage by rank
+            const int nmax = __reduce_max_sync(FSLIC_FULL, min(n_g, AS_LIST));
+            for (int a0 = 0; a0 < nmax; a0 += 8) {
+                const int a = a0 + gl;
+                const bool mine = a < n_g && n_g <= AS_LIST;
+                const uint32_t key = mine ? s_ukey[grp][a] : 0u;
+                int rank = 0;
+                for (int u = 0; u < nmax; u++) rank += (u < n_g) && (s_ukey[grp][u] < key);
+                if (mine) {
+                    const int32_t cyx = s_ucyx[grp][a];
+                    const int cy = (int16_t)(cyx & 0xffff), cx = cyx >> 16;
+                    s_ent[grp][rank] =
+                        make_uint2(s_ucol[grp][a], (uint32_t)(2 * ((ap.OY - cy) * TS + (ap.OX - cx))));
+                    s_k[grp][rank] = (uint16_t)(key & 0xffff);
+                }
             }
-            continue;
         }
-        // ---- sort by (phase, k): rank by counting (keys are unique) ----
-        for (int t = tid; t < n; t += AS_THREADS) {
-            const uint32_t key = s_ukey[t];
-            int rank = 0;
-            for (int u = 0; u < n; u++) rank += (s_ukey[u] < key);
-            const int32_t cyx = s_ucyx[t];
-            const int cy = (int16_t)(cyx & 0xffff), cx = cyx >> 16;
-            s_ent[rank] = make_uint2(s_ucol[t], (uint32_t)((ap.OY - cy) * ap.TS + (ap.OX - cx)));
-            s_cyx[rank] = cyx;
-            s_k[rank] = (uint16_t)(key & 0xffff);
+        __syncwarp();
+        if (UPDATE) {
+            // constant feature rows of the MMA A operand: 1 (count), row index 0..3, lane index (data rows per tile)
+            *reinterpret_cast<uint4*>(&s_feat[lane][0]) =
+                make_uint4(0x01010101u, 0x03020100u, (uint32_t)lane * 0x01010101u, 0u);
+            *reinterpret_cast<uint2*>(&s_feat[lane][6]) = make_uint2(0u, 0u);
         }
-        __syncthreads();
 
-        // ---- per-warp footprint ----
-        const int wj0 = tj0 + wx * 32;
-        const int wsr0 = tsr0 + wy * R;
-        if (wj0 < W && wsr0 < ap.nsub) {  // warp-uniform
-            const int wsr1 = min(wsr0 + R, ap.nsub) - 1;
-            const int wi0 = ap.rem + wsr0 * ap.stride, wi1 = ap.rem + wsr1 * ap.stride;
+        // ---- the 4 tiles, one after the other ----
+#pragma unroll 1
+        for (int tq = 0; tq < AS_T; tq++) {
+            const int tx = sx * AS_T + tq;
+            if (tx >= ap.tiles_x) break;  // warp uniform
+            const int n = __shfl_sync(FSLIC_FULL, n_g, tq * 8);
+            const int wj0 = tx * 32;
             const int j = wj0 + lane;
             const bool colok = j < W;
-            const uint32_t* qd = quad + (size_t)b * H * W;
-            uint16_t* lb = labels + (size_t)b * H * W;
+            const uint32_t* qrow = quad + img_off + (size_t)wi0 * W + j;  // this lane's pixel in row 0 of the tile
+            uint16_t* lrow = labels + img_off + (size_t)wi0 * W + j;
 
-            uint32_t q[R], best[R];
-            int pixoff[R];
+            // ---- 1. pixels ----
+            uint32_t q[R];
 #pragma unroll
             for (int rr = 0; rr < R; rr++) {
-                const int i = wi0 + rr * ap.stride;
-                const bool ok = colok && (wsr0 + rr < ap.nsub);
-                q[rr] = ok ? ld_nc_u32(qd + (size_t)i * W + j) : 0u;
-                // invalid lanes alias the warp origin so every patch address stays in range
-                pixoff[rr] = ok ? (i * ap.TS + j) : (wi0 * ap.TS + wj0);
-                best[rr] = 0xffffffffu;
+                const bool ok = colok && rr < nrow;
+                q[rr] = ok ? ld_nc_u32(qrow + rr * rowpix) : 0u;
             }
 
-            for (int base = 0; base < n; base += 32) {
-                const int c = base + lane;
-                bool hit = false;
-                if (c < n) {
-                    const int32_t cyx = s_cyx[c];
-                    const int cy = (int16_t)(cyx & 0xffff), cx = cyx >> 16;
-                    hit = (cy >= wi0 - S) && (cy <= wi1 + S) && (cx >= wj0 - S) && (cx <= wj0 + 31 + S);
-                }
-                unsigned m = __ballot_sync(FSLIC_FULL, hit);
-                while (m) {
-                    const int bit = __ffs(m) - 1;
-                    m &= m - 1;
-                    const int cidx = base + bit;
-                    const uint2 e = s_ent[cidx];
+            if (n > AS_LIST) {
+                // ---- overflow (clusters piled on one spot): brute force, direct atomics ----
 #pragma unroll
-                    for (int rr = 0; rr < R; rr++) {
-                        const uint32_t sp = s_tbl[(int)e.y + pixoff[rr]];
-                        const uint32_t d = sad4_acc(q[rr], e.x, sp);
-                        best[rr] = min(best[rr], d * 65536u + (uint32_t)cidx);
+                for (int rr = 0; rr < R; rr++) {
+                    if (colok && rr < nrow) {
+                        const int i = wi0 + rr * stride;
+                        const uint32_t label = assign_pixel_generic(ap, i, j, q[rr], ci, cs, labels + img_off);
+                        if (UPDATE && label != 0xFFFF) acc_add_pixel(ac, label, i, j, q[rr]);
                     }
                 }
+                continue;
             }
 
-            // ---- labels + update ----
-            uint32_t* ac = acc + (size_t)b * ap.K * 6;
+            // ---- 2. distances ----
+            // every (row, column) of the footprint is inside the patch for every listed candidate, valid or not.
+            // patch entry of (row rr, candidate c) at shared byte address row0 + c.offset + rr * 2*stride*TS
+            const unsigned char* rowp = smem_raw + 2 * (wi0 * TS + j);
+            uint32_t best[R];
+#pragma unroll
+            for (int rr = 0; rr < R; rr++) best[rr] = 0xffffffffu;
+            for (int c = 0; c < n; c++) {
+                const uint2 e = s_ent[tq][c];
+                const unsigned char* pc = rowp + (int)e.y;
+#pragma unroll
+                for (int rr = 0; rr < R; rr++) {
+                    const uint32_t sp = *reinterpret_cast<const uint16_t*>(pc + rr * (2 * stride * TS));
+                    const uint32_t d = sad4_acc(q[rr], e.x, sp);
+                    best[rr] = min(best[rr], d * 65536u + (uint32_t)c);
+                }
+            }
+
+            // ---- 3. labels ----
+            uint32_t rw = 0;  // local rank bytes of this lane's R pixels (0xFF = contributes to no candidate)
 #pragma unroll
             for (int rr = 0; rr < R; rr++) {
-                const int i = wi0 + rr * ap.stride;
-                const bool ok = colok && (wsr0 + rr < ap.nsub);
+                const bool ok = colok && rr < nrow;
                 const bool covered = ok && ((best[rr] >> 16) < FSLIC_BIGSP);
-                const int rank = (int)(best[rr] & 0xffff);
+                uint32_t rb = 0xff;
                 if (covered) {
-                    lb[(size_t)i * W + j] = s_k[rank];
+                    rb = best[rr] & 0xff;
+                    lrow[rr * rowpix] = s_k[tq][rb];
                 } else if (ok) {
-                    const bool fresh = (i % ap.cfg_stride) >= ap.fresh_from;
-                    if (fresh) {
-                        lb[(size_t)i * W + j] = 0xFFFF;
+                    const int i = wi0 + rr * stride;
+                    if ((i % ap.cfg_stride) >= ap.fresh_from) {
+                        lrow[rr * rowpix] = 0xFFFF;
                     } else if (UPDATE) {  // a stale label from an earlier pass still counts (context.cpp:318-319)
-                        const uint16_t old = lb[(size_t)i * W + j];
-                        if (old != 0xFFFF) {
-                            atomicAdd(&ac[old * 6 + 0], 1u);
-                            atomicAdd(&ac[old * 6 + 1], (uint32_t)i);
-                            atomicAdd(&ac[old * 6 + 2], (uint32_t)j);
-                            atomicAdd(&ac[old * 6 + 3], q[rr] & 0xff);
-                            atomicAdd(&ac[old * 6 + 4], (q[rr] >> 8) & 0xff);
-                            atomicAdd(&ac[old * 6 + 5], (q[rr] >> 16) & 0xff);
+                        const uint16_t old = lrow[rr * rowpix];
+                        if (old != 0xFFFF) acc_add_pixel(ac, old, i, j, q[rr]);
+                    }
+                }
+                rw |= rb << (8 * rr);
+            }
+
+            // ---- 4. update sums on the tensor cores ----
+            if (UPDATE) {
+                // transpose this lane's 4 quads into per-channel words (byte rr = row rr)
+                const uint32_t lo01 = __byte_perm(q[0], q[1], 0x5140), lo23 = __byte_perm(q[2], q[3], 0x5140);
+                const uint32_t hi01 = __byte_perm(q[0], q[1], 0x0062), hi23 = __byte_perm(q[2], q[3], 0x0062);
+                s_feat[lane][3] = __byte_perm(lo01, lo23, 0x5410);  // L
+                *reinterpret_cast<uint2*>(&s_feat[lane][4]) =
+                    make_uint2(__byte_perm(lo01, lo23, 0x7632), __byte_perm(hi01, hi23, 0x5410));  // a, b
+                __syncwarp();
+                for (int nt = 0; nt * 8 < n; nt++) {
+                    // D[feature][candidate] += A[feature][pixel] * B[pixel][candidate];  rows 8..15 of A are zero
+                    int d[4] = {0, 0, 0, 0};
+                    const uint32_t mg = (uint32_t)(nt * 8 + g) * 0x01010101u;
+#pragma unroll
+                    for (int s4 = 0; s4 < 4; s4++) {
+                        const uint32_t w0 = __shfl_sync(FSLIC_FULL, rw, 8 * s4 + tig);
+                        const uint32_t w1 = __shfl_sync(FSLIC_FULL, rw, 8 * s4 + 4 + tig);
+                        const uint32_t a0 = s_feat[8 * s4 + tig][g];
+                        const uint32_t a2 = s_feat[8 * s4 + 4 + tig][g];
+                        mma_u8_16x8x32(d, a0, 0u, a2, 0u, eq80(w0, mg), eq80(w1, mg));
+                    }
+                    // lane (g, tig): feature g of candidates nt*8 + 2*tig (d0) and +1 (d1), scaled by 128.
+                    //   features: 0 n | 1 sum(row idx) | 2 sum(lane idx) | 3 sum L | 4 sum a | 5 sum b
+#pragma unroll
+                    for (int hh = 0; hh < 2; hh++) {
+                        const int c = nt * 8 + 2 * tig + hh;
+                        const uint32_t v = (uint32_t)d[hh] >> 7;
+                        const uint32_t partner = __shfl_down_sync(FSLIC_FULL, v, 4);  // feature g+1, same candidate
+                        const uint32_t cnt = __shfl_sync(FSLIC_FULL, v, tig);        // feature 0, same candidate
+                        if (c < n && cnt > 0 && g < 6 && (g & 1) == 0) {
+                            unsigned long long word;
+                            if (g == 0)
+                                word = (unsigned long long)cnt |
+                                       ((unsigned long long)(cnt * (uint32_t)wi0 + (uint32_t)stride * partner) << 32);
+                            else if (g == 2)
+                                word = (unsigned long long)(cnt * (uint32_t)wj0 + v) | ((unsigned long long)partner << 32);
+                            else
+                                word = (unsigned long long)v | ((unsigned long long)partner << 32);
+                            atomicAdd(&ac[(int)s_k[tq][c] * 4 + (g >> 1)], word);
                         }
                     }
                 }
-                if (UPDATE) {
-                    unsigned act = __ballot_sync(FSLIC_FULL, covered);
-                    const uint32_t w0 = (q[rr] & 0xff) | ((q[rr] & 0xff00) << 8);        // L | a << 16
-                    const uint32_t w1 = ((q[rr] >> 16) & 0xff) | ((uint32_t)lane << 16);  // b | lane << 16
-                    while (act) {
-                        const int src = __ffs(act) - 1;
-                        const int r0 = __shfl_sync(FSLIC_FULL, rank, src);
-                        const bool mine = covered && rank == r0;
-                        const unsigned mm = __ballot_sync(FSLIC_FULL, mine);
-                        if (mine) {
-                            const uint32_t s0 = __reduce_add_sync(mm, w0);
-                            const uint32_t s1 = __reduce_add_sync(mm, w1);
-                            if (lane == src) {
-                                const uint32_t cnt = __popc(mm);
-                                uint32_t* sa = &s_acc[r0 * 6];
-                                atomicAdd(&sa[0], cnt);
-                                atomicAdd(&sa[1], cnt * (uint32_t)i);
-                                atomicAdd(&sa[2], cnt * (uint32_t)wj0 + (s1 >> 16));
-                                atomicAdd(&sa[3], s0 & 0xffff);
-                                atomicAdd(&sa[4], s0 >> 16);
-                                atomicAdd(&sa[5], s1 & 0xffff);
-                            }
-                        }
-                        act &= ~mm;
-                    }
-                }
+                __syncwarp();  // s_feat is rewritten by the next tile
             }
         }
-        if (UPDATE) {
-            __syncthreads();
-            uint32_t* ac = acc + (size_t)b * ap.K * 6;
-            for (int t = tid; t < n * 6; t += AS_THREADS) {
-                const uint32_t v = s_acc[t];
-                if (v) atomicAdd(&ac[(int)s_k[t / 6] * 6 + (t % 6)], v);
-            }
-        }
+        __syncwarp();  // the list staging is rewritten by the next super tile
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_assign_generic<UPDATE>: correctness-first path without the shared-memory patch or tile lists.
-// Used (a) for whole passes when S is so large that the linear patch does not fit in shared memory,
-// (b) for the few tiles whose candidate list overflowed AS_NC (clusters piled on one spot).
-// One thread per pixel; walks the cell grid; lexicographic minimum of (d, phase, k) in a u64 key.
+// k_assign_generic<UPDATE>: correctness-first path without the shared-memory patch, for S so large
+// that the linear patch does not fit in shared memory.  One thread per pixel.
 // ---------------------------------------------------------------------------------------------
 template <bool UPDATE>
 __global__ void __launch_bounds__(256) k_assign_generic(AssignParams ap, const uint32_t* __restrict__ quad,
                                                          uint16_t* __restrict__ labels,
                                                          const CInfo* __restrict__ cinfo,
                                                          const int* __restrict__ cell_start,
-                                                         const int* __restrict__ cell_items,
-                                                         uint32_t* __restrict__ acc,
-                                                         const int* __restrict__ tile_list, int R) {
-    // tile_list == nullptr: blockIdx.x enumerates all tiles of all images; else tile_list[0] = count
-    const long count = tile_list ? (long)tile_list[0] : (long)ap.ntiles * ap.B;
-    for (long idx = blockIdx.x; idx < count; idx += gridDim.x) {
-    const long tile = tile_list ? (long)tile_list[1 + idx] : idx;
-    const int b = (int)(tile / ap.ntiles);
-    const int tl = (int)(tile - (long)b * ap.ntiles);
-    const int ty = tl / ap.tiles_x, tx = tl - ty * ap.tiles_x;
-    const int tj0 = tx * (AS_WX * 32), tsr0 = ty * (AS_WY * R);
-    const int nrows = AS_WY * R, ncols = AS_WX * 32;
-    const int S = ap.S, W = ap.W, H = ap.H;
-    const CInfo* ci = cinfo + (size_t)b * ap.K;
-    const int* cs = cell_start + (size_t)b * (ap.ncell + 1);
-    const int* items = cell_items + (size_t)b * ap.K;
-    const uint32_t* qd = quad + (size_t)b * H * W;
-    uint16_t* lb = labels + (size_t)b * H * W;
-    uint32_t* ac = acc + (size_t)b * ap.K * 6;
-    for (int t = threadIdx.x; t < nrows * ncols; t += blockDim.x) {
-        const int sr = tsr0 + t / ncols, j = tj0 + t % ncols;
-        if (sr >= ap.nsub || j >= W) continue;
+                                                         unsigned long long* __restrict__ acc) {
+    const long per_img = (long)ap.nsub * ap.W;
+    const long total = per_img * ap.B;
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+        const int b = (int)(t / per_img);
+        const long r = t - (long)b * per_img;
+        const int sr = (int)(r / ap.W), j = (int)(r - (long)sr * ap.W);
         const int i = ap.rem + sr * ap.stride;
-        const uint32_t q = qd[(size_t)i * W + j];
-        unsigned long long best = ~0ull;
-        const int cr0 = max(i - S, 0) / ap.G, cr1 = min(i + S, H - 1) / ap.G;
-        const int cc0 = max(j - S, 0) / ap.G, cc1 = min(j + S, W - 1) / ap.G;
-        for (int cr = cr0; cr <= cr1; cr++) {
-            const int s = cs[cr * ap.cellW + cc0], e = cs[cr * ap.cellW + cc1 + 1];
-            for (int u = s; u < e; u++) {
-                const CInfo r = ci[items[u]];
-                const int cy = (int16_t)(r.cyx & 0xffff), cx = r.cyx >> 16;
-                const int di = abs(i - cy), dj = abs(j - cx);
-                if (di > S || dj > S) continue;
-                const uint32_t sp = (uint16_t)__float2uint_rz(__fmul_rn(ap.coef, (float)(di + dj)));
-                const uint32_t d = sad4_acc(q, r.color, sp) & 0xffffu;  // u16 arithmetic like the scalar reference
-                const unsigned long long key = ((unsigned long long)d << 32) | r.sortkey;
-                best = key < best ? key : best;
-            }
-        }
-        uint32_t label;
-        if (best != ~0ull && (uint32_t)(best >> 32) < 0xFFFFu) {
-            label = (uint32_t)(best & 0xffff);
-            lb[(size_t)i * W + j] = (uint16_t)label;
-        } else {
-            const bool fresh = (i % ap.cfg_stride) >= ap.fresh_from;
-            if (fresh) {
-                lb[(size_t)i * W + j] = 0xFFFF;
-                label = 0xFFFF;
-            } else {
-                label = lb[(size_t)i * W + j];
-            }
-        }
-        if (UPDATE && label != 0xFFFF) {
-            atomicAdd(&ac[label * 6 + 0], 1u);
-            atomicAdd(&ac[label * 6 + 1], (uint32_t)i);
-            atomicAdd(&ac[label * 6 + 2], (uint32_t)j);
-            atomicAdd(&ac[label * 6 + 3], q & 0xff);
-            atomicAdd(&ac[label * 6 + 4], (q >> 8) & 0xff);
-            atomicAdd(&ac[label * 6 + 5], (q >> 16) & 0xff);
-        }
-    }
+        const uint32_t q = quad[(size_t)b * ap.H * ap.W + (size_t)i * ap.W + j];
+        const uint32_t label = assign_pixel_generic(ap, i, j, q, cinfo + (size_t)b * ap.K,
+                                                    cell_start + (size_t)b * (ap.ncell + 1),
+                                                    labels + (size_t)b * ap.H * ap.W);
+        if (UPDATE && label != 0xFFFF) acc_add_pixel(acc + (size_t)b * ap.K * 4, label, i, j, q);
     }
 }

@@ -13,6 +13,12 @@
 #include "common.cuh"
 #include "lab.cuh"
 
+#define SPT_MAX_ELEMS (128 * 1024)  // u16 elements per spatial patch buffer
+
+typedef void (*assign_fn)(AssignParams, const uint32_t*, uint16_t*, const CInfo*, const int*, unsigned long long*,
+                          const uint16_t*);
+static assign_fn pick_assign(int TS, int stride, bool update);
+
 static thread_local std::string g_err;
 static int set_err(int code, const std::string& msg) {
     g_err = msg;
@@ -35,13 +41,11 @@ struct fslic_ctx {
     uint32_t* quad = nullptr;      // [B][N]   Lab quad image
     uint16_t* labels = nullptr;    // [B][N]   pre-CCA labels
     CInfo* cinfo = nullptr;        // [B][K]
-    uint32_t* acc = nullptr;       // [B][K][6]
+    unsigned long long* acc = nullptr;  // [B][K][4] packed sums (assign.cuh)
     int* cell_start = nullptr;     // [B][ncell+1]
-    int* cell_items = nullptr;     // [B][K]
-    uint16_t* sptable = nullptr;   // linear spatial patch
-    int* overflow = nullptr;       // [1 + maxB*ntiles_max]
+    CInfo* cinfo_tmp = nullptr;    // [B][K] scratch of k_prepare (records by cluster index)
+    uint16_t* sptable = nullptr;   // two linear spatial patches: [0] subsampled passes, [1] full pass
     int G = 1, cellW = 1, cellH = 1, ncell = 1;
-    size_t overflow_cap = 0;
     // cca state (sized for cca_batch images at a time)
     int cca_batch = 1;
     int* par = nullptr;            // [Bc][N]
@@ -111,7 +115,7 @@ extern "C" int fslic_b200_destroy(fslic_ctx* c) {
     if (!c) return FSLIC_OK;
     cudaSetDevice(c->device);
     void* ptrs[] = {c->d_gamma, c->d_labtbl, c->quad,   c->labels,  c->cinfo,  c->acc,    c->cell_start,
-                    c->cell_items, c->sptable, c->overflow, c->par,  c->aux,    c->cleader, c->carea,
+                    c->cinfo_tmp, c->sptable, c->par,  c->aux,    c->cleader, c->carea,
                     c->cnew,    c->fin,      c->blkcnt, c->blkoff,  c->counters, c->heap, c->d_img,
                     c->d_cl,    c->d_lab};
     for (void* p : ptrs)
@@ -165,21 +169,18 @@ extern "C" int fslic_b200_create(int device, int H, int W, int K, int max_batch,
     CKC(cudaMemcpy(c->d_labtbl, labtbl.data(), 8193 * 2, cudaMemcpyHostToDevice));
 
     // candidate cell grid: pitch G >= max(S,1), at most ~16K cells so the histogram fits in smem
-    int G = c->S > 0 ? c->S : 1;
+    int G = c->S > 2 ? c->S : 2;  // >= 2 so that ceil(2^32/G) fits 32 bits (div_g)
     while ((long)ceil_div(H, G) * ceil_div(W, G) > 16000) G++;
     c->G = G; c->cellW = ceil_div(W, G); c->cellH = ceil_div(H, G); c->ncell = c->cellW * c->cellH;
 
     CKC(dalloc(&c->quad, B * N));
     CKC(dalloc(&c->labels, B * N));
     CKC(dalloc(&c->cinfo, B * K));
-    CKC(dalloc(&c->acc, B * K * 6));
-    CKC(cudaMemset(c->acc, 0, B * K * 6 * sizeof(uint32_t)));
+    CKC(dalloc(&c->acc, B * K * 4));
+    CKC(cudaMemset(c->acc, 0, B * K * 4 * sizeof(unsigned long long)));
     CKC(dalloc(&c->cell_start, B * (c->ncell + 1)));
-    CKC(dalloc(&c->cell_items, B * K));
-    CKC(dalloc(&c->sptable, (size_t)256 * 1024));  // up to 512 KB of patch (only <= smem-sized ones are used)
-    // worst-case tile count: full pass with the smallest tile height (R = 1 -> 4 rows)
-    c->overflow_cap = B * (size_t)ceil_div(W, AS_WX * 32) * (size_t)ceil_div(H, AS_WY) + 1;
-    CKC(dalloc(&c->overflow, c->overflow_cap + 1));
+    CKC(dalloc(&c->cinfo_tmp, B * K));
+    CKC(dalloc(&c->sptable, (size_t)2 * SPT_MAX_ELEMS));
 
     // CCA scratch: 22 B/pixel/image; cap the resident set at ~12 GB
     const size_t per_img = N * 22 + 4096;
@@ -197,16 +198,17 @@ extern "C" int fslic_b200_create(int device, int H, int W, int K, int max_batch,
     CKC(dalloc(&c->blkcnt, bc * nblk));
     CKC(dalloc(&c->blkoff, bc * nblk));
     CKC(dalloc(&c->counters, bc));
-    c->heap_K = 65536;
+    c->heap_K = 65536 + 8;
     CKC(dalloc(&c->heap, bc * (size_t)c->heap_K));
     for (auto& e : c->ev) CKC(cudaEventCreate(&e));
     CKC(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
 
     // opt in to large dynamic shared memory once
-    CKC(cudaFuncSetAttribute(k_assign_tiles<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin - 20 * 1024));
-    CKC(cudaFuncSetAttribute(k_assign_tiles<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin - 20 * 1024));
-    CKC(cudaFuncSetAttribute(k_assign_tiles<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin - 20 * 1024));
-    CKC(cudaFuncSetAttribute(k_assign_tiles<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin - 20 * 1024));
+    for (int ts : {128, 192, 256, 384})
+        for (int stride : {0, 1, 3})
+            for (int upd = 0; upd < 2; upd++)
+                CKC(cudaFuncSetAttribute(pick_assign(ts, stride, upd != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         c->max_smem_optin - 1024));
     CKC(cudaFuncSetAttribute(k_cca_select, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin - 40 * 1024));
     CKC(cudaFuncSetAttribute(k_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
     *out = c;
@@ -257,21 +259,29 @@ static int run_cca(fslic_ctx* c, const uint16_t* d_in, uint16_t* d_out, int batc
     CcaParams cp;
     cp.H = c->H; cp.W = c->W; cp.N = N; cp.K = K; cp.thres = thres;
     cp.nblk = ceil_div(N, CCA_BLOCK);
-    const size_t heap_bytes = (size_t)K * 8;
+    const size_t heap_bytes = (size_t)(K + 2) * 8;
     cp.heap_in_smem = heap_bytes <= (size_t)(c->max_smem_optin - 40 * 1024);
-    if (K > c->heap_K) return set_err(FSLIC_EINVAL, "K too large for the selection heap");
+    if (K + 2 > c->heap_K) return set_err(FSLIC_EINVAL, "K too large for the selection heap");
     for (int b0 = 0; b0 < batch; b0 += c->cca_batch) {
         const int nb = (batch - b0 < c->cca_batch) ? (batch - b0) : c->cca_batch;
         const uint16_t* in = d_in + (size_t)b0 * N;
         uint16_t* out = d_out + (size_t)b0 * N;
         CK(cudaMemsetAsync(c->counters, 0, sizeof(CcaCounters) * nb, st));
         dim3 g(cp.nblk, nb);
-        k_ccl_init<<<g, CCA_BLOCK, 0, st>>>(cp, in, c->par, c->aux);
-        k_ccl_merge<<<g, CCA_BLOCK, 0, st>>>(cp, in, c->par);
+        dim3 gt(ceil_div(c->W, CCL_T), ceil_div(c->H, CCL_T), nb);
+        k_ccl_tile<<<gt, CCL_T * CCL_T, 0, st>>>(cp, in, c->par, c->aux);
+        {
+            const int seam_px = ((c->W - 1) / CCL_T) * c->H + ((c->H - 1) / CCL_T) * c->W;
+            if (seam_px > 0) {
+                dim3 gs(ceil_div(seam_px, 256), nb);
+                k_ccl_seams<<<gs, 256, 0, st>>>(cp, in, c->par);
+            }
+        }
         k_ccl_flatten<<<g, CCA_BLOCK, 0, st>>>(cp, in, c->par, c->aux, c->blkcnt);
         k_scan_blocks<<<nb, 1024, 0, st>>>(c->blkcnt, c->blkoff, cp.nblk, cp.nblk, nullptr, 0, 1,
                                            &c->counters[0].ncomp, (int)(sizeof(CcaCounters) / sizeof(int)));
         k_ccl_number<<<g, CCA_BLOCK, 0, st>>>(cp, c->par, c->aux, c->blkoff, c->cleader, c->carea, c->counters);
+        k_cca_threshold<<<nb, 1024, 0, st>>>(cp, c->carea, c->counters);
         k_cca_select<<<nb, 1024, cp.heap_in_smem ? heap_bytes : 0, st>>>(cp, c->carea, c->counters, c->heap);
         k_kept_count<<<g, CCA_BLOCK, 0, st>>>(cp, c->carea, c->counters, c->blkcnt);
         k_scan_blocks<<<nb, 1024, 0, st>>>(c->blkcnt, c->blkoff, cp.nblk, 0, &c->counters[0].ncomp,
@@ -285,7 +295,7 @@ static int run_cca(fslic_ctx* c, const uint16_t* d_in, uint16_t* d_out, int batc
         dim3 go(ob, nb);
         k_cca_output<<<go, 256, 0, st>>>(cp, c->par, c->fin, out);
         CK(cudaGetLastError());
-        if (launches) *launches += 11;
+        if (launches) *launches += 12;
     }
     return FSLIC_OK;
 }
@@ -302,7 +312,7 @@ extern "C" int fslic_b200_enforce_connectivity(fslic_ctx* c, uint16_t* d_labels,
 extern "C" int fslic_b200_debug_heap_select(fslic_ctx* c, const int32_t* d_area, int n, int middle, uint8_t* d_kept,
                                             void* stream) {
     if (!c) return set_err(FSLIC_EINVAL, "ctx is NULL");
-    if (middle > c->heap_K || middle < 1 || n < 1) return set_err(FSLIC_EINVAL, "bad n/middle");
+    if (middle + 2 > c->heap_K || middle < 1 || n < 1) return set_err(FSLIC_EINVAL, "bad n/middle");
     CK(cudaSetDevice(c->device));
     CK(cudaMemsetAsync(d_kept, 0, n, (cudaStream_t)stream));
     k_debug_heap_select<<<1, 1024, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint32_t*>(d_area), n, middle,
@@ -311,7 +321,7 @@ extern "C" int fslic_b200_debug_heap_select(fslic_ctx* c, const int32_t* d_area,
     return FSLIC_OK;
 }
 
-// ---- one assign pass (fast tiles kernel + generic fallback) ---------------------------------------
+// ---- one assign pass (warp kernel, or the generic kernel when the patch cannot live in shared memory) ----
 struct PassGeom {
     int R;
     bool fast;
@@ -322,14 +332,49 @@ struct PassGeom {
 static PassGeom pass_geometry(const fslic_ctx* c, int stride) {
     PassGeom g;
     const int S = c->S;
-    g.R = 4;
+    g.R = AS_R;
     g.OX = S + 31;
     g.OY = S + stride * (g.R - 1);
-    g.TS = 2 * g.OX + 2;  // even row pitch
-    g.tbl_elems = (2 * g.OY + 1) * g.TS;
-    g.smem = align_up((size_t)g.tbl_elems * 2, 16);
-    g.fast = g.smem <= (size_t)(c->max_smem_optin - 24 * 1024) && g.tbl_elems <= 256 * 1024;
+    // row pitch from a fixed menu so it is a compile-time constant of the kernel (immediate LDS offsets)
+    const int need = 2 * g.OX + 1;
+    g.TS = need <= 128 ? 128 : need <= 192 ? 192 : need <= 256 ? 256 : need <= 384 ? 384 : 0;
+    const long elems = (long)(2 * g.OY + 1) * (g.TS ? g.TS : need);
+    g.tbl_elems = (int)(elems < (1L << 30) ? elems : (1L << 30));
+    g.smem = align_up((size_t)g.tbl_elems * 2, 16) + AS_STAGE_BYTES;
+    g.fast = g.TS != 0 && elems <= SPT_MAX_ELEMS && g.smem <= (size_t)(c->max_smem_optin - 2 * 1024);
     return g;
+}
+
+// kernel menu: TS in {128,192,256,384} x (STRIDE 3 + update | STRIDE 1 no update | runtime stride)
+template <int TS>
+static assign_fn pick_assign_ts(int stride, bool update) {
+    if (update) return stride == 3 ? k_assign_warp<TS, 3, true> : k_assign_warp<TS, 0, true>;
+    return stride == 1 ? k_assign_warp<TS, 1, false> : k_assign_warp<TS, 0, false>;
+}
+static assign_fn pick_assign(int TS, int stride, bool update) {
+    switch (TS) {
+        case 128: return pick_assign_ts<128>(stride, update);
+        case 192: return pick_assign_ts<192>(stride, update);
+        case 256: return pick_assign_ts<256>(stride, update);
+        default: return pick_assign_ts<384>(stride, update);
+    }
+}
+
+static int build_patches(fslic_ctx* c, int stride, bool need_sub, float coef, cudaStream_t st, int* launches) {
+    if (need_sub) {
+        const PassGeom g = pass_geometry(c, stride);
+        if (g.fast) {
+            k_build_sptable<<<64, 256, 0, st>>>(c->sptable, c->S, g.OY, g.OX, g.TS, coef);
+            if (launches) *launches += 1;
+        }
+    }
+    const PassGeom gf = pass_geometry(c, 1);
+    if (gf.fast) {
+        k_build_sptable<<<64, 256, 0, st>>>(c->sptable + SPT_MAX_ELEMS, c->S, gf.OY, gf.OX, gf.TS, coef);
+        if (launches) *launches += 1;
+    }
+    CK(cudaGetLastError());
+    return FSLIC_OK;
 }
 
 static int run_assign_pass(fslic_ctx* c, int batch, int stride, int rem, int cfg_stride, int fresh_from, bool update,
@@ -342,23 +387,22 @@ static int run_assign_pass(fslic_ctx* c, int batch, int stride, int rem, int cfg
     if (ap.nsub <= 0) return FSLIC_OK;
     ap.cfg_stride = cfg_stride; ap.fresh_from = fresh_from;
     ap.G = c->G; ap.cellW = c->cellW; ap.cellH = c->cellH; ap.ncell = c->ncell;
+    ap.Ginv = (uint32_t)(((1ull << 32) + (unsigned)c->G - 1) / (unsigned)c->G);
     ap.OY = g.OY; ap.OX = g.OX; ap.TS = g.TS; ap.tbl_elems = g.tbl_elems;
-    ap.tiles_x = ceil_div(c->W, AS_WX * 32);
-    ap.tiles_y = ceil_div(ap.nsub, AS_WY * g.R);
+    ap.tiles_x = ceil_div(c->W, 32);
+    ap.tiles_y = ceil_div(ap.nsub, g.R);
     ap.ntiles = ap.tiles_x * ap.tiles_y;
     ap.coef = coef;
-    const long total = (long)ap.ntiles * batch;
     if (g.fast) {
-        k_build_sptable<<<64, 256, 0, st>>>(c->sptable, c->S, g.OY, g.OX, g.TS, coef);
-        CK(cudaMemsetAsync(c->overflow, 0, sizeof(int), st));
+        const uint16_t* tbl = c->sptable + (update ? 0 : SPT_MAX_ELEMS);
+        const assign_fn fn = pick_assign(g.TS, stride, update);
         int occ = 1;
-        if (update)
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_assign_tiles<4, true>, AS_THREADS, g.smem);
-        else
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_assign_tiles<4, false>, AS_THREADS, g.smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, AS_THREADS, g.smem);
         if (occ < 1) occ = 1;
         long grid = (long)c->num_sms * occ;
-        if (grid > total) grid = total;
+        const long supers = (long)ceil_div(ap.tiles_x, AS_T) * ap.tiles_y * batch;
+        const long need = (supers + AS_WARPS - 1) / AS_WARPS;
+        if (grid > need) grid = need;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (c->kev_on && update) {
             while ((int)c->kev.size() < c->kev_used + 2) {
@@ -370,31 +414,20 @@ static int run_assign_pass(fslic_ctx* c, int batch, int stride, int rem, int cfg
             e1 = c->kev[c->kev_used++];
             CK(cudaEventRecord(e0, st));
         }
-        if (update)
-            k_assign_tiles<4, true><<<(int)grid, AS_THREADS, g.smem, st>>>(ap, c->quad, c->labels, c->cinfo, c->cell_start,
-                                                                           c->cell_items, c->acc, c->sptable, c->overflow);
-        else
-            k_assign_tiles<4, false><<<(int)grid, AS_THREADS, g.smem, st>>>(ap, c->quad, c->labels, c->cinfo, c->cell_start,
-                                                                            c->cell_items, c->acc, c->sptable, c->overflow);
+        fn<<<(int)grid, AS_THREADS, g.smem, st>>>(ap, c->quad, c->labels, c->cinfo, c->cell_start, c->acc, tbl);
         if (e1) CK(cudaEventRecord(e1, st));
-        // overflowed tiles (normally none): generic kernel over the recorded list, grid sized for a modest count
-        int og = (int)(total < 4096 ? total : 4096);
-        if (update)
-            k_assign_generic<true><<<og, 256, 0, st>>>(ap, c->quad, c->labels, c->cinfo, c->cell_start, c->cell_items,
-                                                       c->acc, c->overflow, g.R);
-        else
-            k_assign_generic<false><<<og, 256, 0, st>>>(ap, c->quad, c->labels, c->cinfo, c->cell_start, c->cell_items,
-                                                        c->acc, c->overflow, g.R);
-        if (launches) *launches += 3;
     } else {
+        const long px = (long)ap.nsub * c->W * batch;
+        long grid = (px + 255) / 256;
+        if (grid > (long)c->num_sms * 64) grid = (long)c->num_sms * 64;
         if (update)
-            k_assign_generic<true><<<(int)total, 256, 0, st>>>(ap, c->quad, c->labels, c->cinfo, c->cell_start,
-                                                               c->cell_items, c->acc, nullptr, g.R);
+            k_assign_generic<true><<<(int)grid, 256, 0, st>>>(ap, c->quad, c->labels, c->cinfo, c->cell_start,
+                                                              c->acc);
         else
-            k_assign_generic<false><<<(int)total, 256, 0, st>>>(ap, c->quad, c->labels, c->cinfo, c->cell_start,
-                                                                c->cell_items, c->acc, nullptr, g.R);
-        if (launches) *launches += 1;
+            k_assign_generic<false><<<(int)grid, 256, 0, st>>>(ap, c->quad, c->labels, c->cinfo, c->cell_start,
+                                                               c->acc);
     }
+    if (launches) *launches += 1;
     CK(cudaGetLastError());
     return FSLIC_OK;
 }
@@ -406,7 +439,7 @@ static int run_prepare(fslic_ctx* c, fslic_cluster* d_clusters, int batch, int f
     pp.G = c->G; pp.cellW = c->cellW; pp.cellH = c->cellH; pp.ncell = c->ncell;
     pp.first = first; pp.finalize = finalize; pp.last = 0;
     const size_t smem = (size_t)(c->ncell + 2) * sizeof(int);
-    k_prepare<<<batch, 1024, smem, st>>>(pp, d_clusters, c->acc, c->quad, c->cinfo, c->cell_start, c->cell_items);
+    k_prepare<<<batch, 1024, smem, st>>>(pp, d_clusters, c->acc, c->quad, c->cinfo, c->cell_start, c->cinfo_tmp);
     CK(cudaGetLastError());
     if (launches) *launches += 1;
     return FSLIC_OK;
@@ -440,6 +473,8 @@ extern "C" int fslic_b200_iterate(fslic_ctx* c, const uint8_t* d_images, fslic_c
     launches++;
     if (timing) CK(cudaEventRecord(c->ev[1], st));
     const int stride = p->subsample_stride;
+    rc = build_patches(c, stride, p->max_iter > 0, coef, st, &launches);
+    if (rc) return rc;
     int rem = 0;
     for (int it = 0; it < p->max_iter; it++) {
         rc = run_prepare(c, d_clusters, batch, it == 0, it > 0, st, &launches);

@@ -4,10 +4,10 @@
 // DisjointSet::flatten (/root/reference/src/cca.cpp:33-101, 103-173, 178-265; cca.h:36-57).
 //
 // Pipeline (all kernels batched over images with blockIdx.y):
-//   k_ccl_init     parent[p] = first pixel of p's run inside its 32-pixel chunk
-//   k_ccl_merge    lock-free union (atomicMin on roots) across chunk seams and between rows; the
-//                  representative of a set is always its MINIMUM raster index == the reference's
-//                  "leader" (cca.h:38-55 merges towards the smaller index)
+//   k_ccl_tile     union-find of every 32 x 32 tile in shared memory; parent[p] = tile-local root
+//   k_ccl_seams    lock-free union (atomicMin on roots) across the tile seams; the representative
+//                  of a set is always its MINIMUM raster index == the reference's "leader"
+//                  (cca.h:38-55 merges towards the smaller index)
 //   k_ccl_flatten  parent[p] = root; per-root area (run-aggregated atomics); roots per block
 //   k_scan_blocks  exclusive scan of the per-block counts (one CTA per image)
 //   k_ccl_number   component number = rank of the root in raster order (cca.cpp:118-134);
@@ -37,7 +37,10 @@ struct CcaCounters {
     int ncomp;
     int ncand;
     int nkept;
-    int sel_mode;  // 1: selection ran, kept flag = top bit of carea
+    int sel_mode;  // 0: kept <=> area >= keep_thres; 1: selection ran, kept flag = top bit of carea
+    int keep_thres;
+    int need_sim;  // 1: the K-th largest area is tied ambiguously -> replay std::partial_sort step by step
+    int pad0, pad1;
 };
 
 __device__ __forceinline__ int ccl_find(const int* par, int x) {
@@ -66,47 +69,100 @@ __device__ __forceinline__ void ccl_union(int* par, int a, int b) {
     }
 }
 
-__global__ void __launch_bounds__(CCA_BLOCK) k_ccl_init(CcaParams cp, const uint16_t* __restrict__ labels,
-                                                        int* __restrict__ par, uint32_t* __restrict__ area_at) {
-    const int b = blockIdx.y;
-    const int p = blockIdx.x * CCA_BLOCK + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    const uint16_t* lab = labels + (size_t)b * cp.N;
-    const bool ok = p < cp.N;
-    const uint32_t v = ok ? lab[p] : 0x10000u;
-    const uint32_t left = __shfl_up_sync(FSLIC_FULL, v, 1);
-    const int j = ok ? (p % cp.W) : 0;
-    const bool start = (lane == 0) || (j == 0) || (v != left);
-    const unsigned m = __ballot_sync(FSLIC_FULL, start);
-    const int s = 31 - __clz(m & (0xffffffffu >> (31 - lane)));
-    if (ok) {
-        par[(size_t)b * cp.N + p] = p - (lane - s);
-        area_at[(size_t)b * cp.N + p] = 0;
+// ---- level 1: union-find of one 32 x 32 pixel tile entirely in shared memory -----------------------
+// One thread per pixel, one warp per tile row.  Runs inside a row come from a ballot; vertical links are
+// united with shared-memory atomicMin (only where a run overlap starts); every pixel then points at the
+// tile-local root (minimum raster index inside the tile), written as a GLOBAL raster index.
+#define CCL_T 32
+__device__ __forceinline__ int ccl_find_s(const int* par, int x) {
+    int p = par[x];
+    while (p != x) {
+        x = p;
+        p = par[x];
+    }
+    return x;
+}
+__device__ __forceinline__ void ccl_union_s(int* par, int a, int b) {
+    a = ccl_find_s(par, a);
+    b = ccl_find_s(par, b);
+    while (a != b) {
+        if (a < b) {
+            int t = a;
+            a = b;
+            b = t;
+        }
+        const int old = atomicMin(&par[a], b);
+        if (old == a) break;
+        a = ccl_find_s(par, old);
+        b = ccl_find_s(par, b);
     }
 }
 
-__global__ void __launch_bounds__(CCA_BLOCK) k_ccl_merge(CcaParams cp, const uint16_t* __restrict__ labels,
-                                                         int* __restrict__ par_all) {
+__global__ void __launch_bounds__(CCL_T * CCL_T) k_ccl_tile(CcaParams cp, const uint16_t* __restrict__ labels,
+                                                             int* __restrict__ par_all,
+                                                             uint32_t* __restrict__ area_all) {
+    __shared__ uint32_t s_lab[CCL_T][CCL_T + 1];
+    __shared__ int s_par[CCL_T * CCL_T];
+    const int b = blockIdx.z;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int j = blockIdx.x * CCL_T + tx, i = blockIdx.y * CCL_T + ty;
+    const bool ok = (i < cp.H) && (j < cp.W);
+    const int p = i * cp.W + j;
+    // invalid pixels get labels that differ from everything (and from each other along a row / column)
+    const uint32_t v = ok ? (uint32_t)labels[(size_t)b * cp.N + p] : (0x10000u + (uint32_t)threadIdx.x);
+    s_lab[ty][tx] = v;
+    const uint32_t left = __shfl_up_sync(FSLIC_FULL, v, 1);
+    const bool start = (tx == 0) || (v != left);
+    const unsigned m = __ballot_sync(FSLIC_FULL, start);
+    const int sl = 31 - __clz(m & (0xffffffffu >> (31 - tx)));
+    const int me = ty * CCL_T + tx;
+    s_par[me] = ty * CCL_T + sl;
+    __syncthreads();
+    if (ty > 0) {
+        const uint32_t up = s_lab[ty - 1][tx];
+        if (up == v) {
+            // (me, up) is implied by the pair one pixel to the left when both runs extend there
+            bool need = (tx == 0) || (left != v);
+            if (!need) need = s_lab[ty - 1][tx - 1] != up;
+            if (need) ccl_union_s(s_par, me - CCL_T, me);
+        }
+    }
+    __syncthreads();
+    if (ok) {
+        const int r = ccl_find_s(s_par, me);
+        const int ri = blockIdx.y * CCL_T + (r >> 5), rj = blockIdx.x * CCL_T + (r & 31);
+        par_all[(size_t)b * cp.N + p] = ri * cp.W + rj;
+        area_all[(size_t)b * cp.N + p] = 0;
+    }
+}
+
+// ---- level 2: unite tiles across their seams with the global lock-free union ------------------------
+// index space per image: [0, nV) pixels on vertical seams (columns j = 32, 64, ..), then [nV, nV+nH)
+// pixels on horizontal seams (rows i = 32, 64, ..).
+__global__ void __launch_bounds__(256) k_ccl_seams(CcaParams cp, const uint16_t* __restrict__ labels,
+                                                   int* __restrict__ par_all) {
     const int b = blockIdx.y;
-    const int p = blockIdx.x * CCA_BLOCK + threadIdx.x;
-    if (p >= cp.N) return;
-    const int lane = threadIdx.x & 31;
+    const int W = cp.W, H = cp.H;
+    const int sv = (W - 1) / CCL_T, sh = (H - 1) / CCL_T;  // number of vertical / horizontal seams
+    const int nV = sv * H, nH = sh * W;
     const uint16_t* lab = labels + (size_t)b * cp.N;
     int* par = par_all + (size_t)b * cp.N;
-    const int W = cp.W;
-    const int j = p % W;
-    const uint16_t v = lab[p];
-    const bool has_left = j > 0, has_up = p >= W;
-    const uint16_t left = has_left ? lab[p - 1] : 0;
-    // seam between two 32-pixel chunks of the same row
-    if (lane == 0 && has_left && left == v) ccl_union(par, p - 1, p);
-    if (has_up) {
-        const uint16_t up = lab[p - W];
-        if (up == v) {
-            // the pair (p, up) is implied by (p-1, up-1) when both runs extend to the left
-            bool need = !has_left || left != v;
-            if (!need) need = lab[p - W - 1] != up;
-            if (need) ccl_union(par, p - W, p);
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nV + nH; t += gridDim.x * blockDim.x) {
+        if (t < nV) {
+            const int i = t / sv, j = (t - i * sv + 1) * CCL_T;
+            const int p = i * W + j;
+            if (lab[p - 1] == lab[p]) ccl_union(par, p - 1, p);
+        } else {
+            const int u = t - nV;
+            const int r = u / W, j = u - r * W;
+            const int i = (r + 1) * CCL_T;
+            const int p = i * W + j;
+            const uint16_t v = lab[p], up = lab[p - W];
+            if (up == v) {
+                bool need = (j % CCL_T == 0) || (lab[p - 1] != v);
+                if (!need) need = lab[p - W - 1] != up;
+                if (need) ccl_union(par, p - W, p);
+            }
         }
     }
 }
@@ -243,6 +299,118 @@ __global__ void __launch_bounds__(CCA_BLOCK) k_ccl_number(CcaParams cp, const in
 }
 
 // ---------------------------------------------------------------------------------------------
+// k_cca_threshold: decides, per image, what "the K largest candidates" are without replaying the
+// heap whenever that is unambiguous.  Candidates are components with area >= thres (cca.cpp:213-219).
+//   * ncand <= K: every candidate is kept (cca.cpp:225 is not taken)           -> keep_thres = thres
+//   * else: t = K-th largest candidate area (exact 3 x 11-bit radix select), G = #(area > t),
+//     E = #(area == t).  std::partial_sort keeps all G and K-G of the E tied ones; when E == K-G the
+//     kept SET is simply {area >= t}                                             -> keep_thres = t
+//   * otherwise the choice among the tied components depends on libstdc++'s heap dynamics
+//                                                                                -> need_sim = 1
+// One CTA per image, streaming the area array three times (4 B x ncomp, L2 resident).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_cca_threshold(CcaParams cp, const uint32_t* __restrict__ carea_all,
+                                                        CcaCounters* __restrict__ counters) {
+    __shared__ unsigned int s_hist[2048];
+    __shared__ int s_warp[32];
+    __shared__ unsigned int s_prefix, s_rank, s_found_bin, s_found_cnt;
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    CcaCounters* ct = &counters[b];
+    const int ncomp = ct->ncomp, ncand = ct->ncand;
+    if (ncand <= cp.K) {
+        if (tid == 0) {
+            ct->keep_thres = cp.thres;
+            ct->sel_mode = 0;
+            ct->need_sim = 0;
+        }
+        return;
+    }
+    const uint32_t* area = carea_all + (size_t)b * cp.N;
+    if (tid == 0) {
+        s_prefix = 0;
+        s_rank = (unsigned)cp.K;  // rank (1-based, from the top) still to locate inside the current prefix bucket
+    }
+    unsigned last_E = 0;
+    for (int pass = 0; pass < 3; pass++) {
+        const int shift = 22 - 11 * pass;
+        for (int t = tid; t < 2048; t += 1024) s_hist[t] = 0;
+        __syncthreads();
+        const unsigned prefix = s_prefix;
+        for (int base = 0; base < ncomp; base += 1024) {
+            const int c = base + tid;
+            bool act = false;
+            unsigned bin = 0;
+            if (c < ncomp) {
+                const uint32_t a = area[c];
+                act = ((int)a >= cp.thres) && ((pass == 0) || ((a >> (shift + 11)) == prefix));
+                bin = (a >> shift) & 2047u;
+            }
+            // skew-aware histogram: the lanes that share the first active lane's bin add once
+            unsigned am = __ballot_sync(FSLIC_FULL, act);
+            if (am) {
+                const int src = __ffs(am) - 1;
+                const unsigned b0 = __shfl_sync(FSLIC_FULL, bin, src);
+                const unsigned same = __ballot_sync(FSLIC_FULL, act && bin == b0);
+                if (lane == src) atomicAdd(&s_hist[b0], __popc(same));
+                if (act && bin != b0) atomicAdd(&s_hist[bin], 1u);
+            }
+        }
+        __syncthreads();
+        // locate the bin holding the s_rank-th largest: inclusive scan from the top bin downwards
+        const unsigned rank = s_rank;
+        const int r0 = 2 * tid;  // reversed bins r0, r0+1  <->  bins 2047-r0, 2046-r0
+        const unsigned h0 = s_hist[2047 - r0], h1 = s_hist[2046 - r0];
+        unsigned x = h0 + h1;
+        const unsigned mine = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned y = __shfl_up_sync(FSLIC_FULL, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_warp[warp] = (int)x;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned w = (unsigned)s_warp[lane];
+            unsigned z = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned y = __shfl_up_sync(FSLIC_FULL, z, o);
+                if (lane >= o) z += y;
+            }
+            s_warp[lane] = (int)(z - w);
+        }
+        __syncthreads();
+        const unsigned before = (unsigned)s_warp[warp] + x - mine;  // candidates in bins above this thread's pair
+        if (before < rank && before + h0 >= rank) {
+            s_found_bin = 2047 - r0;
+            s_found_cnt = before;
+        } else if (before + h0 < rank && before + h0 + h1 >= rank) {
+            s_found_bin = 2046 - r0;
+            s_found_cnt = before + h0;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            s_prefix = (prefix << 11) | s_found_bin;
+            s_rank = rank - s_found_cnt;
+        }
+        last_E = s_hist[s_found_bin];
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const unsigned t = s_prefix;           // K-th largest candidate area
+        const unsigned need = s_rank;          // how many of the tied (== t) components are kept: K - G
+        if (last_E == need) {
+            ct->keep_thres = (int)t;
+            ct->sel_mode = 0;
+            ct->need_sim = 0;
+        } else {
+            ct->need_sim = 1;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // std::partial_sort(comps.begin(), comps.begin()+K, comps.end(), area-descending) -- the SET it leaves
 // in the first K slots (cca.cpp:225-228), libstdc++ bits/stl_heap.h semantics.  The heap holds
 // (area << 32 | component) words; only the area takes part in comparisons, like the reference's
@@ -256,34 +424,42 @@ __global__ void __launch_bounds__(CCA_BLOCK) k_ccl_number(CcaParams cp, const in
 
 __device__ __forceinline__ uint32_t hs_area(unsigned long long e) { return (uint32_t)(e >> 32); }
 
-__device__ void hs_push_heap(unsigned long long* h, int hole, int top, unsigned long long value) {
-    int parent = (hole - 1) / 2;
-    while (hole > top && hs_area(h[parent]) > hs_area(value)) {
-        h[hole] = h[parent];
-        hole = parent;
-        parent = (hole - 1) / 2;
+// The heap array is stored with a +1 slot offset (element i at h[i + 1]) so that the two children of a
+// node (2i+1, 2i+2 -> slots 2i+2, 2i+3) form one aligned 16-byte pair: one LDS.128 / LDG.128 per level.
+// h must hold len + 2 slots and be 16-byte aligned.
+//
+// __adjust_heap(first, hole, len, value) of bits/stl_heap.h walks the hole down to a leaf (child with the
+// smaller area; on equal areas the RIGHT child), then __push_heap walks the value back up while
+// area[parent] > area[value].  Along a root-to-leaf path of a valid heap the areas never decrease, so the
+// value ends directly above the first path element whose area exceeds it: the same final arrangement is
+// produced by this top-down walk that stops early -- it visits the same children in the same order.
+__device__ __forceinline__ void hs_adjust_heap(unsigned long long* h, int hole, int len, unsigned long long value) {
+    const uint32_t va = hs_area(value);
+    int l = 2 * hole + 1;
+    if (l < len) {
+        ulonglong2 pr = *reinterpret_cast<const ulonglong2*>(&h[l + 1]);  // children of the hole
+        for (;;) {
+            // prefetch the children of both children (one level ahead) so the next level's LDS latency
+            // overlaps this level's decision; slots beyond len + 1 are never dereferenced
+            ulonglong2 g0 = pr, g1 = pr;
+            const int ll = 2 * l + 1;  // left child of l; children of l+1 start at ll + 2
+            if (ll < len) g0 = *reinterpret_cast<const ulonglong2*>(&h[ll + 1]);
+            if (ll + 2 < len) g1 = *reinterpret_cast<const ulonglong2*>(&h[ll + 3]);
+            const bool take_left = (l + 1 >= len) || (hs_area(pr.y) > hs_area(pr.x));  // right unless right > left
+            const unsigned long long cv = take_left ? pr.x : pr.y;
+            if (hs_area(cv) > va) break;
+            h[hole + 1] = cv;
+            hole = take_left ? l : l + 1;
+            l = 2 * hole + 1;
+            if (l >= len) break;
+            pr = take_left ? g0 : g1;
+        }
     }
-    h[hole] = value;
-}
-__device__ void hs_adjust_heap(unsigned long long* h, int hole, int len, unsigned long long value) {
-    const int top = hole;
-    int child = hole;
-    while (child < (len - 1) / 2) {
-        child = 2 * (child + 1);
-        if (hs_area(h[child]) > hs_area(h[child - 1])) child--;
-        h[hole] = h[child];
-        hole = child;
-    }
-    if ((len & 1) == 0 && child == (len - 2) / 2) {
-        child = 2 * (child + 1);
-        h[hole] = h[child - 1];
-        hole = child - 1;
-    }
-    hs_push_heap(h, hole, top, value);
+    h[hole + 1] = value;
 }
 
 // generic body shared by the pipeline kernel and the debug entry point
-__device__ void heap_select_body(const uint32_t* __restrict__ area, int ncomp, int K, int thres,
+__device__ __forceinline__ void heap_select_body(const uint32_t* __restrict__ area, int ncomp, int K, int thres,
                                  unsigned long long* heap, uint32_t* __restrict__ mark_out /* |= 1<<31 */,
                                  uint8_t* __restrict__ kept_bytes /* or nullptr */) {
     __shared__ unsigned long long s_queue[SEL_CHUNK];
@@ -340,7 +516,7 @@ __device__ void heap_select_body(const uint32_t* __restrict__ area, int ncomp, i
         int consumed = 0;
         if (filling) {
             consumed = min(qn, K - filled);
-            for (int u = tid; u < consumed; u += nt) heap[filled + u] = s_queue[u];
+            for (int u = tid; u < consumed; u += nt) heap[filled + u + 1] = s_queue[u];
             __syncthreads();
         }
         if (tid == 0) {
@@ -349,7 +525,7 @@ __device__ void heap_select_body(const uint32_t* __restrict__ area, int ncomp, i
                 if (K >= 2) {
                     int parent = (K - 2) / 2;
                     for (;;) {
-                        const unsigned long long value = heap[parent];
+                        const unsigned long long value = heap[parent + 1];
                         hs_adjust_heap(heap, parent, K, value);
                         if (parent == 0) break;
                         parent--;
@@ -360,9 +536,9 @@ __device__ void heap_select_body(const uint32_t* __restrict__ area, int ncomp, i
                 // phase 2: the rest, one by one (cca.cpp:226 -> __heap_select loop)
                 for (int u = consumed; u < qn; u++) {
                     const unsigned long long e = s_queue[u];
-                    if (hs_area(e) > hs_area(heap[0])) hs_adjust_heap(heap, 0, K, e);  // __pop_heap(first, middle, i)
+                    if (hs_area(e) > hs_area(heap[1])) hs_adjust_heap(heap, 0, K, e);  // __pop_heap(first, middle, i)
                 }
-                s_min = hs_area(heap[0]);
+                s_min = hs_area(heap[1]);
             }
             s_filled = f;
         }
@@ -371,7 +547,7 @@ __device__ void heap_select_body(const uint32_t* __restrict__ area, int ncomp, i
     // publish the selected set
     const int filled = s_filled;
     for (int u = tid; u < filled; u += nt) {
-        const uint32_t c = (uint32_t)(heap[u] & 0xffffffffu);
+        const uint32_t c = (uint32_t)(heap[u + 1] & 0xffffffffu);
         if (mark_out) mark_out[c] |= 0x80000000u;
         if (kept_bytes) kept_bytes[c] = 1;
     }
@@ -383,11 +559,12 @@ __global__ void __launch_bounds__(1024) k_cca_select(CcaParams cp, uint32_t* __r
     extern __shared__ __align__(16) unsigned char sel_smem[];
     const int b = blockIdx.x;
     CcaCounters* ct = &counters[b];
-    if (ct->ncand <= cp.K) return;  // cca.cpp:225: nothing to select
-    unsigned long long* heap = cp.heap_in_smem ? reinterpret_cast<unsigned long long*>(sel_smem)
-                                               : heap_global + (size_t)b * cp.K;
-    heap_select_body(carea_all + (size_t)b * cp.N, ct->ncomp, cp.K, cp.thres, heap,
-                     carea_all + (size_t)b * cp.N, nullptr);
+    if (!ct->need_sim) return;  // k_cca_threshold settled it (or cca.cpp:225 is not taken)
+    uint32_t* area = carea_all + (size_t)b * cp.N;
+    if (cp.heap_in_smem)
+        heap_select_body(area, ct->ncomp, cp.K, cp.thres, reinterpret_cast<unsigned long long*>(sel_smem), area, nullptr);
+    else
+        heap_select_body(area, ct->ncomp, cp.K, cp.thres, heap_global + (size_t)b * ((cp.K + 3) & ~1), area, nullptr);
     if (threadIdx.x == 0) ct->sel_mode = 1;
 }
 
@@ -397,8 +574,8 @@ __global__ void __launch_bounds__(1024) k_debug_heap_select(const uint32_t* __re
     heap_select_body(area, n, middle, 0, heap_global, nullptr, kept);
 }
 
-__device__ __forceinline__ bool cca_is_kept(uint32_t a, int sel_mode, int thres) {
-    return sel_mode ? (a >> 31) : ((int)a >= thres);
+__device__ __forceinline__ bool cca_is_kept(uint32_t a, int sel_mode, int keep_thres) {
+    return sel_mode ? (a >> 31) : ((int)a >= keep_thres);
 }
 
 __global__ void __launch_bounds__(CCA_BLOCK) k_kept_count(CcaParams cp, const uint32_t* __restrict__ carea_all,
@@ -411,7 +588,7 @@ __global__ void __launch_bounds__(CCA_BLOCK) k_kept_count(CcaParams cp, const ui
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
     const int c = blockIdx.x * CCA_BLOCK + threadIdx.x;
-    const bool kept = (c < ncomp) && cca_is_kept(carea_all[(size_t)b * cp.N + c], counters[b].sel_mode, cp.thres);
+    const bool kept = (c < ncomp) && cca_is_kept(carea_all[(size_t)b * cp.N + c], counters[b].sel_mode, counters[b].keep_thres);
     const unsigned m = __ballot_sync(FSLIC_FULL, kept);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(&s_cnt, __popc(m));
     __syncthreads();
@@ -429,7 +606,7 @@ __global__ void __launch_bounds__(CCA_BLOCK) k_kept_label(CcaParams cp, const ui
     if (blockIdx.x * CCA_BLOCK >= ncomp) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c = blockIdx.x * CCA_BLOCK + tid;
-    const bool kept = (c < ncomp) && cca_is_kept(carea_all[(size_t)b * cp.N + c], counters[b].sel_mode, cp.thres);
+    const bool kept = (c < ncomp) && cca_is_kept(carea_all[(size_t)b * cp.N + c], counters[b].sel_mode, counters[b].keep_thres);
     const unsigned m = __ballot_sync(FSLIC_FULL, kept);
     if (lane == 0) s_warp[warp] = __popc(m);
     __syncthreads();
