@@ -15,7 +15,7 @@ EXPORTED_SYMBOLS = (
     "fslic_b200_destroy", "fslic_b200_initialize_clusters", "fslic_b200_iterate", "fslic_b200_iterate_host",
     "fslic_b200_initialize_clusters_host", "fslic_b200_enforce_connectivity", "fslic_b200_debug_stages",
     "fslic_b200_rgb_to_quad", "fslic_b200_debug_heap_select", "fslic_b200_stage_ms", "fslic_b200_get_S",
-    "fslic_b200_launches_last_iterate", "fslic_b200_assign_kernel_time",
+    "fslic_b200_launches_last_iterate", "fslic_b200_assign_kernel_time", "fslic_b200_debug_cca_counters",
 )
 
 STAGE_NAMES = ("cielab_conversion", "assign", "update", "full_assign", "enforce_connectivity", "iterate")
@@ -67,6 +67,7 @@ def lib():
     L.fslic_b200_get_S.argtypes = [vp]
     L.fslic_b200_launches_last_iterate.argtypes = [vp]
     L.fslic_b200_assign_kernel_time.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+    L.fslic_b200_debug_cca_counters.argtypes = [vp, C.POINTER(C.c_int32), i32]
     assert L.fslic_b200_sizeof_cluster() == 32
     _lib = L
     return L

@@ -111,17 +111,23 @@ class SlicModel(object):
     @clusters.setter
     def clusters(self, clusters):
         """cfast_slic.pyx:68-98: yx -> uint16, colour -> uint8, number = index."""
+        def c_uint(v, bits):  # Cython's object -> unsigned C integer conversion: truncates floats, range-checks
+            v = int(v)
+            if v < 0 or v >= (1 << bits):
+                raise OverflowError("value too large to convert to uint%d_t" % bits)
+            return v
+
         new = np.zeros(len(clusters), CLUSTER_DTYPE)
         for i, d in enumerate(clusters):
             y, x = d["yx"]
             r, g, b = d["color"]
             new[i]["number"] = i
-            new[i]["y"] = np.uint16(int(y))
-            new[i]["x"] = np.uint16(int(x))
-            new[i]["r"] = np.uint8(int(r))
-            new[i]["g"] = np.uint8(int(g))
-            new[i]["b"] = np.uint8(int(b))
-            new[i]["num_members"] = np.uint32(int(d["num_members"]))
+            new[i]["y"] = c_uint(y, 16)
+            new[i]["x"] = c_uint(x, 16)
+            new[i]["r"] = c_uint(r, 8)
+            new[i]["g"] = c_uint(g, 8)
+            new[i]["b"] = c_uint(b, 8)
+            new[i]["num_members"] = c_uint(d["num_members"], 32)
             new[i]["is_active"] = 1
             new[i]["is_updatable"] = 1
         self._clusters = new

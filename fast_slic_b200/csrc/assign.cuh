@@ -168,6 +168,7 @@ struct AssignParams {
     uint32_t Ginv;     // ceil(2^32 / G): x / G == __umulhi(x, Ginv) for 0 <= x < 65536 (x * G < 2^32)
     int OY, OX, TS, tbl_elems;
     int tiles_x, tiles_y, ntiles;  // warp tiles (32 columns x R sub-rows) per image
+    int tps;           // warp tiles per super tile: AS_T, or 1 when the launch is too small to fill the GPU otherwise
     float coef;        // generic path only
 };
 
@@ -300,7 +301,8 @@ __global__ void __launch_bounds__(AS_THREADS, 2) k_assign_warp(AssignParams ap, 
     const int rowpix = stride * W;
 
     // super-tile walk without divisions: (b, ty, sx) advance by a fixed (db, dty, dsx) with carries
-    const int stx = (ap.tiles_x + AS_T - 1) / AS_T;  // super tiles per tile row
+    const int tps = ap.tps;
+    const int stx = (ap.tiles_x + tps - 1) / tps;  // super tiles per tile row
     const long per_img = (long)stx * ap.tiles_y;
     const long total = per_img * ap.B;
     const long wstride = (long)gridDim.x * AS_WARPS;
@@ -324,8 +326,8 @@ __global__ void __launch_bounds__(AS_THREADS, 2) k_assign_warp(AssignParams ap, 
 
         // ---- L. candidate lists of the 4 tiles, 8 lanes each ----
         // tile of this lane group: columns [gj0, gj0+31]; wanted clusters: cy in [wi0-S, wi1+S], cx in [gj0-S, gj0+31+S]
-        const int gtx = sx * AS_T + grp;
-        const bool gvalid = gtx < ap.tiles_x;
+        const int gtx = sx * tps + grp;
+        const bool gvalid = grp < tps && gtx < ap.tiles_x;
         const int gj0 = gtx * 32;
         int n_g = 0;  // candidates found for this group's tile (same value in its 8 lanes)
         {
@@ -400,8 +402,8 @@ __global__ void __launch_bounds__(AS_THREADS, 2) k_assign_warp(AssignParams ap, 
 
         // ---- the 4 tiles, one after the other ----
 #pragma unroll 1
-        for (int tq = 0; tq < AS_T; tq++) {
-            const int tx = sx * AS_T + tq;
+        for (int tq = 0; tq < tps; tq++) {
+            const int tx = sx * tps + tq;
             if (tx >= ap.tiles_x) break;  // warp uniform
             const int n = __shfl_sync(FSLIC_FULL, n_g, tq * 8);
             const int wj0 = tx * 32;

@@ -288,7 +288,9 @@ static int run_cca(fslic_ctx* c, const uint16_t* d_in, uint16_t* d_out, int batc
                                            (int)(sizeof(CcaCounters) / sizeof(int)), CCA_BLOCK,
                                            &c->counters[0].nkept, (int)(sizeof(CcaCounters) / sizeof(int)));
         k_kept_label<<<g, CCA_BLOCK, 0, st>>>(cp, c->carea, c->counters, c->blkoff, c->cnew);
-        dim3 ga(ceil_div(N, 256), nb);
+        int ab = ceil_div(N, 256 * 8);
+        if (ab > c->num_sms * 8) ab = c->num_sms * 8;
+        dim3 ga(ab, nb);
         k_cca_absorb<<<ga, 256, 0, st>>>(cp, c->par, c->aux, c->cleader, c->cnew, c->counters, c->fin);
         int ob = ceil_div(N, 256);
         if (ob > c->num_sms * 32) ob = c->num_sms * 32;
@@ -393,6 +395,7 @@ static int run_assign_pass(fslic_ctx* c, int batch, int stride, int rem, int cfg
     ap.tiles_y = ceil_div(ap.nsub, g.R);
     ap.ntiles = ap.tiles_x * ap.tiles_y;
     ap.coef = coef;
+    ap.tps = AS_T;
     if (g.fast) {
         const uint16_t* tbl = c->sptable + (update ? 0 : SPT_MAX_ELEMS);
         const assign_fn fn = pick_assign(g.TS, stride, update);
@@ -400,7 +403,9 @@ static int run_assign_pass(fslic_ctx* c, int batch, int stride, int rem, int cfg
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, AS_THREADS, g.smem);
         if (occ < 1) occ = 1;
         long grid = (long)c->num_sms * occ;
-        const long supers = (long)ceil_div(ap.tiles_x, AS_T) * ap.tiles_y * batch;
+        // small launches (single images): one tile per warp step so that every SM gets work
+        ap.tps = ((long)ap.ntiles * batch < (long)c->num_sms * occ * AS_WARPS * AS_T) ? 1 : AS_T;
+        const long supers = (long)ceil_div(ap.tiles_x, ap.tps) * ap.tiles_y * batch;
         const long need = (supers + AS_WARPS - 1) / AS_WARPS;
         if (grid > need) grid = need;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -518,6 +523,14 @@ extern "C" int fslic_b200_assign_kernel_time(fslic_ctx* c, float* total_ms, int*
     if (!c || !total_ms || !launches) return set_err(FSLIC_EINVAL, "NULL argument");
     *total_ms = c->assign_kernel_ms;
     *launches = c->assign_kernel_launches;
+    return FSLIC_OK;
+}
+
+extern "C" int fslic_b200_debug_cca_counters(fslic_ctx* c, int32_t* out8, int image) {
+    if (!c || !out8 || image < 0 || image >= c->cca_batch) return set_err(FSLIC_EINVAL, "bad argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out8, c->counters + image, sizeof(CcaCounters), cudaMemcpyDeviceToHost));
     return FSLIC_OK;
 }
 

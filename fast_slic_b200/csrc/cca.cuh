@@ -40,7 +40,8 @@ struct CcaCounters {
     int sel_mode;  // 0: kept <=> area >= keep_thres; 1: selection ran, kept flag = top bit of carea
     int keep_thres;
     int need_sim;  // 1: the K-th largest area is tied ambiguously -> replay std::partial_sort step by step
-    int pad0, pad1;
+    int dbg_ops;   // heap replacements performed by k_cca_select (diagnostics)
+    int dbg_t;     // K-th largest candidate area found by k_cca_threshold (diagnostics)
 };
 
 __device__ __forceinline__ int ccl_find(const int* par, int x) {
@@ -332,7 +333,8 @@ __global__ void __launch_bounds__(1024) k_cca_threshold(CcaParams cp, const uint
         s_rank = (unsigned)cp.K;  // rank (1-based, from the top) still to locate inside the current prefix bucket
     }
     unsigned last_E = 0;
-    for (int pass = 0; pass < 3; pass++) {
+    const int first_pass = (cp.N < (1 << 22)) ? 1 : 0;  // areas <= N: the top digit is zero for everything
+    for (int pass = first_pass; pass < 3; pass++) {
         const int shift = 22 - 11 * pass;
         for (int t = tid; t < 2048; t += 1024) s_hist[t] = 0;
         __syncthreads();
@@ -343,7 +345,7 @@ __global__ void __launch_bounds__(1024) k_cca_threshold(CcaParams cp, const uint
             unsigned bin = 0;
             if (c < ncomp) {
                 const uint32_t a = area[c];
-                act = ((int)a >= cp.thres) && ((pass == 0) || ((a >> (shift + 11)) == prefix));
+                act = ((int)a >= cp.thres) && ((pass == first_pass) || ((a >> (shift + 11)) == prefix));
                 bin = (a >> shift) & 2047u;
             }
             // skew-aware histogram: the lanes that share the first active lane's bin add once
@@ -407,6 +409,7 @@ __global__ void __launch_bounds__(1024) k_cca_threshold(CcaParams cp, const uint
         } else {
             ct->need_sim = 1;
         }
+        ct->dbg_t = (int)t;
     }
 }
 
@@ -433,36 +436,60 @@ __device__ __forceinline__ uint32_t hs_area(unsigned long long e) { return (uint
 // area[parent] > area[value].  Along a root-to-leaf path of a valid heap the areas never decrease, so the
 // value ends directly above the first path element whose area exceeds it: the same final arrangement is
 // produced by this top-down walk that stops early -- it visits the same children in the same order.
-__device__ __forceinline__ void hs_adjust_heap(unsigned long long* h, int hole, int len, unsigned long long value) {
-    const uint32_t va = hs_area(value);
-    int l = 2 * hole + 1;
-    if (l < len) {
-        ulonglong2 pr = *reinterpret_cast<const ulonglong2*>(&h[l + 1]);  // children of the hole
-        for (;;) {
-            // prefetch the children of both children (one level ahead) so the next level's LDS latency
-            // overlaps this level's decision; slots beyond len + 1 are never dereferenced
-            ulonglong2 g0 = pr, g1 = pr;
-            const int ll = 2 * l + 1;  // left child of l; children of l+1 start at ll + 2
-            if (ll < len) g0 = *reinterpret_cast<const ulonglong2*>(&h[ll + 1]);
-            if (ll + 2 < len) g1 = *reinterpret_cast<const ulonglong2*>(&h[ll + 3]);
-            const bool take_left = (l + 1 >= len) || (hs_area(pr.y) > hs_area(pr.x));  // right unless right > left
-            const unsigned long long cv = take_left ? pr.x : pr.y;
-            if (hs_area(cv) > va) break;
-            h[hole + 1] = cv;
-            hole = take_left ? l : l + 1;
-            l = 2 * hole + 1;
-            if (l >= len) break;
-            pr = take_left ? g0 : g1;
+// Heap storage accessors: SMEM = explicit shared-window addresses (LDS.128 / STS.64, no generic-address
+// arithmetic on the critical path), otherwise plain global pointers.
+template <bool SMEM>
+struct HeapMem {
+    unsigned long long* g;  // global base (slot 0)
+    uint32_t s;             // shared-window byte address of slot 0
+    __device__ __forceinline__ void pair(int slot, uint32_t& lo0, uint32_t& hi0, uint32_t& lo1, uint32_t& hi1) const {
+        if (SMEM) {
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(lo0), "=r"(hi0), "=r"(lo1), "=r"(hi1) : "r"(s + 8u * (uint32_t)slot));
+        } else {
+            const uint4 v = *reinterpret_cast<const uint4*>(g + slot);
+            lo0 = v.x; hi0 = v.y; lo1 = v.z; hi1 = v.w;
         }
     }
-    h[hole + 1] = value;
+    __device__ __forceinline__ unsigned long long get(int slot) const {
+        if (SMEM) {
+            unsigned long long v;
+            asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(s + 8u * (uint32_t)slot));
+            return v;
+        }
+        return g[slot];
+    }
+    __device__ __forceinline__ void put(int slot, uint32_t lo, uint32_t hi) const {
+        if (SMEM) asm volatile("st.shared.v2.u32 [%0], {%1,%2};" :: "r"(s + 8u * (uint32_t)slot), "r"(lo), "r"(hi) : "memory");
+        else g[slot] = ((unsigned long long)hi << 32) | lo;
+    }
+    __device__ __forceinline__ void put(int slot, unsigned long long v) const { put(slot, (uint32_t)v, (uint32_t)(v >> 32)); }
+};
+
+template <bool SMEM>
+__device__ __forceinline__ void hs_adjust_heap(const HeapMem<SMEM>& h, int hole, int len, unsigned long long value) {
+    const uint32_t va = hs_area(value);
+    for (;;) {
+        const int l = 2 * hole + 1;
+        if (l >= len) break;
+        uint32_t lo0, hi0, lo1, hi1;  // children l (slot l+1) and l+1 (slot l+2): one aligned 16-byte pair
+        h.pair(l + 1, lo0, hi0, lo1, hi1);
+        const bool take_left = (l + 1 >= len) || (hi1 > hi0);  // right unless area[right] > area[left]
+        const uint32_t clo = take_left ? lo0 : lo1, chi = take_left ? hi0 : hi1;
+        if (chi > va) break;
+        h.put(hole + 1, clo, chi);
+        hole = take_left ? l : l + 1;
+    }
+    h.put(hole + 1, value);
 }
 
 // generic body shared by the pipeline kernel and the debug entry point
+template <bool SMEM>
 __device__ __forceinline__ void heap_select_body(const uint32_t* __restrict__ area, int ncomp, int K, int thres,
-                                 unsigned long long* heap, uint32_t* __restrict__ mark_out /* |= 1<<31 */,
-                                 uint8_t* __restrict__ kept_bytes /* or nullptr */) {
-    __shared__ unsigned long long s_queue[SEL_CHUNK];
+                                                  const HeapMem<SMEM> heap, uint32_t* __restrict__ mark_out /* |= 1<<31 */,
+                                                  uint8_t* __restrict__ kept_bytes /* or nullptr */,
+                                                  unsigned long long* s_queue /* shared, SEL_CHUNK entries */,
+                                                  int* dbg_ops = nullptr) {
     __shared__ int s_warp[32];
     __shared__ int s_qn, s_filled;
     __shared__ uint32_t s_min;
@@ -516,38 +543,100 @@ __device__ __forceinline__ void heap_select_body(const uint32_t* __restrict__ ar
         int consumed = 0;
         if (filling) {
             consumed = min(qn, K - filled);
-            for (int u = tid; u < consumed; u += nt) heap[filled + u + 1] = s_queue[u];
+            for (int u = tid; u < consumed; u += nt) heap.put(filled + u + 1, s_queue[u]);
             __syncthreads();
         }
-        if (tid == 0) {
-            int f = filled + consumed;
-            if (filling && f == K) {  // __make_heap(first, middle)
-                if (K >= 2) {
-                    int parent = (K - 2) / 2;
-                    for (;;) {
-                        const unsigned long long value = heap[parent + 1];
-                        hs_adjust_heap(heap, parent, K, value);
-                        if (parent == 0) break;
-                        parent--;
+        const int f = filled + consumed;
+        if (filling && f == K && K >= 2) {
+            // __make_heap(first, middle): __adjust_heap on parents (K-2)/2 .. 0.  Nodes of one tree level
+            // have disjoint subtrees, so a level can be processed in any order (here: in parallel); levels
+            // go bottom-up exactly like the descending parent loop of bits/stl_heap.h.
+            const int last_parent = (K - 2) / 2;
+            int lvl = 31 - __clz(last_parent + 1);  // level of the last parent (root = level 0)
+            for (; lvl >= 0; lvl--) {
+                const int lo = (1 << lvl) - 1, hi = min((2 << lvl) - 2, last_parent);
+                for (int node = lo + tid; node <= hi; node += nt) hs_adjust_heap(heap, node, K, heap.get(node + 1));
+                __syncthreads();
+            }
+        }
+        if (f == K && warp == 0) {
+            // phase 2: the rest of the queue in order (cca.cpp:226 -> __heap_select loop), as a PIPELINE of
+            // sift-downs inside one warp.  Each __pop_heap only ever writes the node it currently stands on
+            // and moves down one level per step, so the next one may start at the root as soon as its
+            // predecessor stands on level >= 2 (node index >= 3): it then reads / writes strictly above
+            // everything the predecessor can still touch.  Lanes are pipeline slots; all advance in lockstep.
+            // Timing is deterministic, so no cross-lane queries are needed: a sift-down moves exactly one
+            // level per half-step (or has finished), one new sift-down may be issued per full step (two
+            // levels behind its predecessor), and `depth` half-steps after the last issue everything is done.
+            bool act = false;
+            int hole = 0;
+            uint32_t vlo = 0, vhi = 0;
+            int qpos = consumed, next_lane = 0, nops = 0;
+            const int depth = 32 - __clz(K);  // levels of the heap: no sift-down takes more half-steps
+            int idle = depth;                 // half-steps since the last issue (start: pipeline empty)
+            auto level_step = [&]() {
+                if (act) {
+                    const int l = 2 * hole + 1;
+                    bool done = l >= K;
+                    if (!done) {
+                        uint32_t lo0, hi0, lo1, hi1;
+                        heap.pair(l + 1, lo0, hi0, lo1, hi1);
+                        const bool take_left = (l + 1 >= K) || (hi1 > hi0);  // right unless area[right] > area[left]
+                        const uint32_t clo = take_left ? lo0 : lo1, chi = take_left ? hi0 : hi1;
+                        if (chi > vhi) {
+                            done = true;
+                        } else {
+                            heap.put(hole + 1, clo, chi);
+                            hole = take_left ? l : l + 1;
+                        }
+                    }
+                    if (done) {
+                        heap.put(hole + 1, vlo, vhi);
+                        act = false;
                     }
                 }
-            }
-            if (f == K) {
-                // phase 2: the rest, one by one (cca.cpp:226 -> __heap_select loop)
-                for (int u = consumed; u < qn; u++) {
-                    const unsigned long long e = s_queue[u];
-                    if (hs_area(e) > hs_area(heap[1])) hs_adjust_heap(heap, 0, K, e);  // __pop_heap(first, middle, i)
+                __syncwarp();
+            };
+            while (qpos < qn || idle < depth) {
+                // ---- issue: the next queue element that beats the root (which its predecessors no longer touch) ----
+                if (qpos < qn) {
+                    const uint32_t root_area = hs_area(heap.get(1));
+                    int tries = 0;
+                    while (qpos < qn && tries < 16) {
+                        const unsigned long long e = s_queue[qpos];
+                        qpos++;
+                        tries++;
+                        if (hs_area(e) > root_area) {  // comp(i, first): __pop_heap(first, middle, i)
+                            if (lane == next_lane) {
+                                act = true;
+                                hole = 0;
+                                vlo = (uint32_t)e;
+                                vhi = (uint32_t)(e >> 32);
+                            }
+                            next_lane = (next_lane + 1) & 31;
+                            nops++;
+                            idle = 0;
+                            break;
+                        }
+                    }
                 }
-                s_min = hs_area(heap[1]);
+                // ---- two levels for every sift-down in flight ----
+                level_step();
+                level_step();
+                idle += 2;
             }
-            s_filled = f;
+            if (lane == 0) {
+                s_min = hs_area(heap.get(1));
+                if (dbg_ops) *dbg_ops += nops;
+            }
         }
+        if (tid == 0) s_filled = f;
         __syncthreads();
     }
     // publish the selected set
     const int filled = s_filled;
     for (int u = tid; u < filled; u += nt) {
-        const uint32_t c = (uint32_t)(heap[u + 1] & 0xffffffffu);
+        const uint32_t c = (uint32_t)(heap.get(u + 1) & 0xffffffffu);
         if (mark_out) mark_out[c] |= 0x80000000u;
         if (kept_bytes) kept_bytes[c] = 1;
     }
@@ -557,21 +646,33 @@ __global__ void __launch_bounds__(1024) k_cca_select(CcaParams cp, uint32_t* __r
                                                      CcaCounters* __restrict__ counters,
                                                      unsigned long long* __restrict__ heap_global) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
+    __shared__ unsigned long long s_queue[SEL_CHUNK];
     const int b = blockIdx.x;
     CcaCounters* ct = &counters[b];
     if (!ct->need_sim) return;  // k_cca_threshold settled it (or cca.cpp:225 is not taken)
     uint32_t* area = carea_all + (size_t)b * cp.N;
-    if (cp.heap_in_smem)
-        heap_select_body(area, ct->ncomp, cp.K, cp.thres, reinterpret_cast<unsigned long long*>(sel_smem), area, nullptr);
-    else
-        heap_select_body(area, ct->ncomp, cp.K, cp.thres, heap_global + (size_t)b * ((cp.K + 3) & ~1), area, nullptr);
+    if (cp.heap_in_smem) {
+        HeapMem<true> hm;
+        hm.g = nullptr;
+        hm.s = (uint32_t)__cvta_generic_to_shared(sel_smem);
+        heap_select_body<true>(area, ct->ncomp, cp.K, cp.thres, hm, area, nullptr, s_queue, &ct->dbg_ops);
+    } else {
+        HeapMem<false> hm;
+        hm.g = heap_global + (size_t)b * ((cp.K + 3) & ~1);
+        hm.s = 0;
+        heap_select_body<false>(area, ct->ncomp, cp.K, cp.thres, hm, area, nullptr, s_queue, &ct->dbg_ops);
+    }
     if (threadIdx.x == 0) ct->sel_mode = 1;
 }
 
 __global__ void __launch_bounds__(1024) k_debug_heap_select(const uint32_t* __restrict__ area, int n, int middle,
                                                             uint8_t* __restrict__ kept,
                                                             unsigned long long* __restrict__ heap_global) {
-    heap_select_body(area, n, middle, 0, heap_global, nullptr, kept);
+    HeapMem<false> hm;
+    hm.g = heap_global;
+    hm.s = 0;
+    __shared__ unsigned long long s_queue[SEL_CHUNK];
+    heap_select_body<false>(area, n, middle, 0, hm, nullptr, kept, s_queue);
 }
 
 __device__ __forceinline__ bool cca_is_kept(uint32_t a, int sel_mode, int keep_thres) {
@@ -637,12 +738,11 @@ __global__ void __launch_bounds__(256) k_cca_absorb(CcaParams cp, const int* __r
                                                     uint16_t* __restrict__ final_all) {
     const int b = blockIdx.y;
     const int ncomp = counters[b].ncomp;
-    const int c0 = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c0 >= ncomp) return;
     const int* par = par_all + (size_t)b * cp.N;
     const uint32_t* aux = aux_all + (size_t)b * cp.N;
     const int* cleader = cleader_all + (size_t)b * cp.N;
     const uint16_t* cnew = cnew_all + (size_t)b * cp.N;
+    for (int c0 = blockIdx.x * blockDim.x + threadIdx.x; c0 < ncomp; c0 += gridDim.x * blockDim.x) {
     int c = c0;
     uint16_t lab = cnew[c];
     while (lab == 0xFFFF) {
@@ -656,6 +756,7 @@ __global__ void __launch_bounds__(256) k_cca_absorb(CcaParams cp, const int* __r
         lab = cnew[c];
     }
     final_all[(size_t)b * cp.N + cleader[c0]] = lab;
+    }
 }
 
 __global__ void __launch_bounds__(256) k_cca_output(CcaParams cp, const int* __restrict__ par_all,

@@ -144,5 +144,10 @@ class Engine:
         check(self._L.fslic_b200_assign_kernel_time(self._h, C.byref(ms), C.byref(n)))
         return float(ms.value), int(n.value)
 
+    def cca_counters(self, image=0):
+        out = (C.c_int32 * 8)()
+        check(self._L.fslic_b200_debug_cca_counters(self._h, out, image))
+        return dict(zip(("ncomp", "ncand", "nkept", "sel_mode", "keep_thres", "need_sim", "heap_ops", "kth_area"), list(out)))
+
     def launches_last_iterate(self):
         return int(self._L.fslic_b200_launches_last_iterate(self._h))

@@ -115,6 +115,10 @@ int fslic_b200_debug_heap_select(fslic_ctx* ctx, const int32_t* d_area, int n, i
  * dominant kernel -- the fused assign+update kernel on the subsampled passes -- in the last iterate(). */
 int fslic_b200_assign_kernel_time(fslic_ctx* ctx, float* total_ms, int* launches);
 
+/* Diagnostics: the 8 int32 CCA counters of image `image` of the last (sub-)batch:
+ * ncomp, ncand, nkept, sel_mode, keep_thres, need_sim, heap_ops, kth_area. */
+int fslic_b200_debug_cca_counters(fslic_ctx* ctx, int32_t* out8, int image);
+
 /* Milliseconds spent per stage in the last iterate() with collect_timing != 0. */
 int fslic_b200_stage_ms(fslic_ctx* ctx, float* out_ms, int count);
 

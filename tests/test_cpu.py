@@ -1,0 +1,232 @@
+"""CPU-only tests (no GPU in this container): the oracle against the golden vectors and the compiled reference,
+the C ABI surface, the host-side logic, and the world_size-2 sharding path over gloo."""
+import ctypes
+import hashlib
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from cases import PIPELINE_CASES, make_image, split_kwargs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden", "golden_v1.npz")
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(GOLDEN)
+
+
+GOLDEN_CASES = [c for c in PIPELINE_CASES if c[2] * c[3] <= 80000]
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES, ids=[c[0] for c in GOLDEN_CASES])
+def test_oracle_matches_golden(port, golden, case):
+    """The plain-C restatement reproduces what the unmodified reference produced (tests/golden/make_golden.py)."""
+    name, kind, H, W, K, kw = case
+    sigma, a = split_kwargs(kw)
+    img = make_image(kind, H, W, seed=7, sigma=sigma)
+    cl = port.initialize(img, K)
+    assert cl.tobytes() == golden[name + "/init"].tobytes()
+    lab, quad, pre = port.iterate(img, cl, a["max_iter"], a["compactness"], a["min_size_factor"],
+                                  a["subsample_stride"], a["convert_to_lab"], stages=True)
+    assert (lab == golden[name + "/labels"]).all()
+    assert cl.tobytes() == golden[name + "/clusters"].tobytes()
+    assert hashlib.sha256(quad.tobytes()).digest() == golden[name + "/quad_sha"].tobytes()
+    assert hashlib.sha256(pre.tobytes()).digest() == golden[name + "/pre_sha"].tobytes()
+
+
+def test_oracle_cca_golden(port, golden):
+    assert (port.enforce_connectivity(golden["cca5/in"], 10, 0) == golden["cca5/out"]).all()
+    for t in range(4):
+        thres, K = golden["cca_rand%d/thres" % t]
+        got = port.enforce_connectivity(golden["cca_rand%d/in" % t], int(K), int(thres))
+        assert (got == golden["cca_rand%d/out" % t]).all()
+
+
+@pytest.mark.parametrize("case", PIPELINE_CASES[:12], ids=[c[0] for c in PIPELINE_CASES[:12]])
+def test_oracle_matches_compiled_reference(port, ref, case):
+    """Live differential test against oracle/_ref (skipped where the reference sources are not available)."""
+    name, kind, H, W, K, kw = case
+    sigma, a = split_kwargs(kw)
+    img = make_image(kind, H, W, seed=13, sigma=sigma)
+    c1, c2 = port.initialize(img, K), ref.initialize(img, K)
+    assert c1.tobytes() == c2.tobytes()
+    args = (a["max_iter"], a["compactness"], a["min_size_factor"], a["subsample_stride"], a["convert_to_lab"])
+    o1, q1, p1 = port.iterate(img, c1, *args, stages=True)
+    o2, q2, p2 = ref.iterate(img, c2, *args, stages=True, num_threads=2)
+    assert (q1 == q2).all() and (p1 == p2).all() and (o1 == o2).all() and c1.tobytes() == c2.tobytes()
+
+
+def test_reference_thread_and_arch_invariance(ref):
+    img = make_image("syn", 120, 160, seed=3)
+    outs = []
+    for arch, nt in (("standard", 1), ("x64/avx2", 1), ("x64/avx2", 3)):
+        cl = ref.initialize(img, 40)
+        outs.append((ref.iterate(img, cl, 10, 10.0, 0.1, 3, True, arch=arch, num_threads=nt).tobytes(), cl.tobytes()))
+    assert outs[0] == outs[1] == outs[2]
+
+
+def test_lab_known_answers(port):
+    """Known answers measured from the reference; the reference's own gtest triples
+    (src/cpptest/test_cielab.cpp:5-37) are for an older un-doubled scale and no longer hold for its own code."""
+    px = np.array([[[139, 91, 30], [255, 255, 255], [255, 255, 0], [0, 0, 0]]], np.uint8)
+    q = port.rgb_to_quad(px, True)[0]
+    assert q[:, :3].tolist() == [[85, 156, 210], [200, 128, 128], [194, 84, 255], [0, 128, 128]]
+    assert (q[:, 3] == 0).all()
+    gamma, lab, cb = port.lab_tables()
+    assert hashlib.sha256(lab.astype("<i4").tobytes()).hexdigest() == \
+        "ee38090c38e046060ca5987d76d797bbf2c71e6519c88e9718dd30e8119c8c56"
+    assert cb.tolist() == [28440, 24656, 12442, 13938, 46868, 4730, 1164, 7175, 57202]
+    assert gamma[0] == 0 and gamma[255] == 8192 and lab.max() == 8192
+
+
+@pytest.mark.parametrize("n,middle,maxarea", [(40, 7, 3), (500, 100, 4), (3000, 1600, 6), (5000, 30, 2), (64, 64, 3)])
+def test_heap_select_port_vs_libstdcxx(port, n, middle, maxarea):
+    """The hand-restated __heap_select against the real std::partial_sort on tie-saturated inputs."""
+    for seed in range(6):
+        rng = np.random.RandomState(seed * 1000 + n)
+        area = rng.randint(1, maxarea + 1, n).astype(np.int32)
+        assert (port.heap_select(area, middle) == port.stl_partial_sort(area, middle)).all()
+
+
+def test_spatial_lut_matches_patch(port):
+    lut = port.spatial_lut(24, 10.0, 1)
+    coef = np.float32(1.0) / (np.float32(24) / np.float32(10.0)) * np.float32(2)
+    want = (coef * np.arange(49, dtype=np.float32)).astype(np.uint16)
+    assert (lut == want).all()
+
+
+# ---- the C ABI ------------------------------------------------------------------------------------------
+def test_abi_library_exports_every_declared_symbol():
+    from fast_slic_b200 import _lib
+    L = _lib.lib()  # loads without a GPU
+    header = open(os.path.join(ROOT, "include", "fslic_b200.h")).read()
+    declared = set(re.findall(r"\b(fslic_b200_\w+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.EXPORTED_SYMBOLS)
+    for sym in declared:
+        assert hasattr(L, sym), sym
+    assert L.fslic_b200_sizeof_cluster() == 32
+    assert L.fslic_b200_version().startswith(b"fast_slic_b200")
+
+
+def test_abi_is_sm100a_only():
+    out = subprocess.run(["cuobjdump", "--list-elf", os.path.join(ROOT, "fast_slic_b200", "libfslic_b200.so")],
+                         capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_cluster_struct_layout():
+    from fast_slic_b200 import CLUSTER_DTYPE
+    offs = {n: CLUSTER_DTYPE.fields[n][1] for n in CLUSTER_DTYPE.names}
+    # == /root/reference/src/fast-slic-common.h:10-23
+    assert offs == {"y": 0, "x": 4, "r": 8, "g": 12, "b": 16, "a": 20, "number": 24, "is_active": 26,
+                    "is_updatable": 27, "num_members": 28}
+    assert CLUSTER_DTYPE.itemsize == 32
+
+
+# ---- host logic (mirrors cfast_slic.pyx error behaviour; no GPU needed) -----------------------------------
+def test_slic_model_argument_errors():
+    from fast_slic_b200 import Slic, SlicModel, get_supported_archs, is_supported_arch, supported_archs
+    assert supported_archs == ("cuda/sm_100a",) and get_supported_archs() == ["cuda/sm_100a"]
+    assert is_supported_arch("cuda/sm_100a") and not is_supported_arch("x64/avx2")
+    with pytest.raises(ValueError):
+        SlicModel(0)
+    with pytest.raises(ValueError):
+        SlicModel(65534)
+    with pytest.raises(NotImplementedError):
+        SlicModel(10, "arm/neon")
+    m = SlicModel(10)
+    with pytest.raises(RuntimeError, match="not initialized"):
+        m.iterate(np.zeros((8, 8, 3), np.uint8), 10, 10.0, 0.25, 3)
+    m.initialized = True
+    with pytest.raises(ValueError, match="nchan != 3"):
+        m.iterate(np.zeros((8, 8, 4), np.uint8), 10, 10.0, 0.25, 3)
+    with pytest.raises(ValueError):
+        m.iterate(np.zeros((8, 8, 3), np.float32), 10, 10.0, 0.25, 3)
+    with pytest.raises(ValueError):
+        m.iterate(np.zeros((8, 16, 3), np.uint8)[:, ::2], 10, 10.0, 0.25, 3)
+    s = Slic(num_components=77, compactness=5, min_size_factor=0.1, convert_to_lab=False)
+    assert s.num_components == 77 and s.convert_to_lab is False and s.last_assignment is None
+    assert s.slic_model.preemptive is False and s.slic_model.manhattan_spatial_dist is True
+
+
+def test_clusters_roundtrip_and_copy():
+    from fast_slic_b200 import SlicModel
+    m = SlicModel(5)
+    with pytest.raises(OverflowError):  # Cython range-checks object -> uint8_t
+        m.clusters = [dict(number=0, yx=(1, 1), color=(300.0, 2.0, 1.0), num_members=4)]
+    cl = [dict(number=9, yx=(3.7, 4.2), color=(200.9, 2.0, 1.0), num_members=4) for _ in range(3)]
+    m.clusters = cl
+    assert m.num_components == 3 and m.initialized
+    got = m.clusters
+    assert [c["number"] for c in got] == [0, 1, 2]          # number = index (cfast_slic.pyx:80)
+    assert got[0]["yx"] == (3.0, 4.0)                          # uint16 truncation (cfast_slic.pyx:69)
+    assert got[0]["color"] == (200.0, 2.0, 1.0)                # uint8 truncation (cfast_slic.pyx:70)
+    c2 = m.copy()
+    assert c2.clusters == got and c2.initialized
+    c2._clusters["y"][0] = 1
+    assert m.clusters[0]["yx"] == (3.0, 4.0)
+
+
+def test_product_never_imports_the_oracle():
+    for fn in os.listdir(os.path.join(ROOT, "fast_slic_b200")):
+        if fn.endswith(".py"):
+            assert "oracle" not in open(os.path.join(ROOT, "fast_slic_b200", fn)).read(), fn
+
+
+def test_requires_cuda_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from fast_slic_b200 import Slic
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Slic(num_components=10).iterate(np.zeros((16, 16, 3), np.uint8))
+
+
+# ---- sharding over gloo, world_size 2 ---------------------------------------------------------------------
+def test_shard_range_partitions():
+    from fast_slic_b200.sharding import shard_range
+    for n in (0, 1, 7, 8, 256, 257):
+        for world in (1, 2, 3, 8):
+            r = [shard_range(n, k, world) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[k][1] == r[k + 1][0] for k in range(world - 1))
+            sizes = [e - s for s, e in r]
+            assert max(sizes) - min(sizes) <= 1
+
+
+_GLOO_SCRIPT = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from fast_slic_b200.sharding import shard_range, gather_labels
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+n_total, H, W = 5, 6, 7
+full = (torch.arange(n_total * H * W, dtype=torch.int32).reshape(n_total, H, W) % 3000).to(torch.int16)
+s, e = shard_range(n_total, rank, world)
+out = gather_labels(full[s:e].clone(), n_total)
+assert out.shape == full.shape and torch.equal(out, full), rank
+t = torch.tensor([float(rank + 1)], dtype=torch.float64)
+dist.all_reduce(t, op=dist.ReduceOp.MAX)      # the max-over-ranks timing reduction bench.py uses
+assert t.item() == world
+dist.barrier()
+print("rank", rank, "ok")
+"""
+
+
+def test_gloo_world_size_2_gather(tmp_path):
+    script = tmp_path / "gloo_gather.py"
+    script.write_text(_GLOO_SCRIPT)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29731", str(script), ROOT],
+                       capture_output=True, text=True, timeout=240, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("ok") == 2

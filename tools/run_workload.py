@@ -28,3 +28,5 @@ for i in range(a.iters):
     torch.cuda.synchronize()
     if a.timing:
         print(eng.stage_ms(), eng.assign_kernel_time())
+for b in range(min(a.batch, 32) if os.environ.get("FSLIC_COUNTERS") else 0):
+    print(b, eng.cca_counters(b))
