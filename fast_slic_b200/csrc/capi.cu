@@ -63,7 +63,8 @@ struct fslic_ctx {
     uint8_t *d_img = nullptr, *h_img = nullptr;
     fslic_cluster *d_cl = nullptr, *h_cl = nullptr;
     uint16_t *d_lab = nullptr, *h_lab = nullptr;
-    cudaStream_t own_stream = nullptr;
+    cudaStream_t own_stream = nullptr, in_stream = nullptr, out_stream = nullptr;
+    std::vector<cudaEvent_t> pipe_ev;  // [2 * chunks]: input-ready / compute-done events of iterate_host
     // timing
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     float stage_ms[FSLIC_T_COUNT] = {0, 0, 0, 0, 0, 0};
@@ -127,6 +128,9 @@ extern "C" int fslic_b200_destroy(fslic_ctx* c) {
         if (e) cudaEventDestroy(e);
     for (auto& e : c->kev) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->in_stream) cudaStreamDestroy(c->in_stream);
+    if (c->out_stream) cudaStreamDestroy(c->out_stream);
+    for (auto& e : c->pipe_ev) cudaEventDestroy(e);
     delete c;
     return FSLIC_OK;
 }
@@ -202,6 +206,8 @@ extern "C" int fslic_b200_create(int device, int H, int W, int K, int max_batch,
     CKC(dalloc(&c->heap, bc * (size_t)c->heap_K));
     for (auto& e : c->ev) CKC(cudaEventCreate(&e));
     CKC(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&c->in_stream, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&c->out_stream, cudaStreamNonBlocking));
 
     // opt in to large dynamic shared memory once
     for (int ts : {128, 192, 256, 384})
@@ -588,15 +594,39 @@ extern "C" int fslic_b200_iterate_host(fslic_ctx* c, const uint8_t* h_images, fs
     CK(cudaSetDevice(c->device));
     rc = ensure_staging(c);
     if (rc) return rc;
-    cudaStream_t st = c->own_stream;
-    const size_t ib = (size_t)batch * c->N * 3, cb = (size_t)batch * c->K * sizeof(fslic_cluster),
-                 lb = (size_t)batch * c->N * 2;
-    CK(cudaMemcpyAsync(c->d_img, h_images, ib, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(c->d_cl, h_clusters, cb, cudaMemcpyHostToDevice, st));
-    rc = fslic_b200_iterate(c, c->d_img, c->d_cl, c->d_lab, batch, p, st);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(h_labels, c->d_lab, lb, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(h_clusters, c->d_cl, cb, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    // Software pipeline over chunks of the batch: H2D(chunk i+1) | compute(chunk i) | D2H(chunk i-1) on three
+    // streams, so for batches the PCIe copies hide behind the kernels (and vice versa).  With pinned host
+    // buffers the copies are truly asynchronous; pageable buffers still work, just without overlap.
+    const size_t N = (size_t)c->N;
+    int chunk = batch <= 4 ? batch : (batch + 3) / 4;
+    if (chunk > 16) chunk = 16;
+    const int nchunks = (batch + chunk - 1) / chunk;
+    while ((int)c->pipe_ev.size() < 2 * nchunks) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->pipe_ev.push_back(e);
+    }
+    fslic_params pp = *p;
+    if (nchunks > 1) pp.collect_timing = 0;  // per-stage timings are only meaningful for an unchunked run
+    for (int k = 0; k < nchunks; k++) {
+        const int b0 = k * chunk, nb = (batch - b0 < chunk) ? (batch - b0) : chunk;
+        CK(cudaMemcpyAsync(c->d_img + (size_t)b0 * N * 3, h_images + (size_t)b0 * N * 3, (size_t)nb * N * 3,
+                           cudaMemcpyHostToDevice, c->in_stream));
+        CK(cudaMemcpyAsync(c->d_cl + (size_t)b0 * c->K, h_clusters + (size_t)b0 * c->K,
+                           (size_t)nb * c->K * sizeof(fslic_cluster), cudaMemcpyHostToDevice, c->in_stream));
+        CK(cudaEventRecord(c->pipe_ev[2 * k], c->in_stream));
+        CK(cudaStreamWaitEvent(c->own_stream, c->pipe_ev[2 * k], 0));
+        rc = fslic_b200_iterate(c, c->d_img + (size_t)b0 * N * 3, c->d_cl + (size_t)b0 * c->K, c->d_lab + (size_t)b0 * N, nb,
+                                &pp, c->own_stream);
+        if (rc) return rc;
+        CK(cudaEventRecord(c->pipe_ev[2 * k + 1], c->own_stream));
+        CK(cudaStreamWaitEvent(c->out_stream, c->pipe_ev[2 * k + 1], 0));
+        CK(cudaMemcpyAsync(h_labels + (size_t)b0 * N, c->d_lab + (size_t)b0 * N, (size_t)nb * N * 2, cudaMemcpyDeviceToHost,
+                           c->out_stream));
+        CK(cudaMemcpyAsync(h_clusters + (size_t)b0 * c->K, c->d_cl + (size_t)b0 * c->K,
+                           (size_t)nb * c->K * sizeof(fslic_cluster), cudaMemcpyDeviceToHost, c->out_stream));
+    }
+    CK(cudaStreamSynchronize(c->out_stream));
+    CK(cudaStreamSynchronize(c->own_stream));
     return FSLIC_OK;
 }
