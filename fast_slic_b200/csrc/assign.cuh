@@ -263,7 +263,8 @@ __device__ __forceinline__ void mma_u8_16x8x32(int (&d)[4], uint32_t a0, uint32_
 //      per cluster that received pixels.  Integer sums are order independent => exact.
 // HBM per processed pixel: 4 B quad read + 2 B label written.
 // ---------------------------------------------------------------------------------------------
-#define AS_R 4   // sub-rows per lane
+#define AS_RG 1  // row groups of 4 sub-rows per lane (R = 4 * AS_RG rows per warp tile)
+#define AS_R (4 * AS_RG)
 #define AS_T 4   // warp tiles per super tile
 #define AS_STAGE_BYTES (AS_WARPS * AS_T * AS_LIST * 22)
 
@@ -289,6 +290,7 @@ __global__ void __launch_bounds__(AS_THREADS, 2) k_assign_warp(AssignParams ap, 
     uint16_t (*s_k)[AS_LIST] = reinterpret_cast<uint16_t (*)[AS_LIST]>(wst + AS_T * AS_LIST * 20);
     uint32_t (*s_feat)[8] = reinterpret_cast<uint32_t (*)[8]>(wst + AS_T * AS_LIST * 8);
     static_assert(32 * 8 * 4 <= AS_T * AS_LIST * 8, "the MMA staging must fit in ukey + ucol");
+    static_assert(AS_R <= 16, "row index feature is a byte and the sums are scaled by 128 in s32");
 
     for (int t = tid; t < (ap.tbl_elems + 1) / 2; t += AS_THREADS)
         reinterpret_cast<uint32_t*>(s_tbl)[t] = reinterpret_cast<const uint32_t*>(g_tbl)[t];
@@ -348,11 +350,11 @@ __global__ void __launch_bounds__(AS_THREADS, 2) k_assign_warp(AssignParams ap, 
                 }
                 const int T = __shfl_sync(FSLIC_FULL, incl, 7, 8);
                 const int Tmax = __reduce_max_sync(FSLIC_FULL, T);
+                const int nr = min(8, cr1 - crb + 1);  // cell rows in this chunk (same for every lane group)
                 for (int t0 = 0; t0 < Tmax; t0 += 8) {
                     const int t = t0 + gl;
                     int row = 0;
-#pragma unroll
-                    for (int r = 0; r < 7; r++) row += (t >= __shfl_sync(FSLIC_FULL, incl, r, 8));
+                    for (int r = 0; r < nr - 1; r++) row += (t >= __shfl_sync(FSLIC_FULL, incl, r, 8));
                     const int rincl = __shfl_sync(FSLIC_FULL, incl, row, 8);
                     const int rcnt = __shfl_sync(FSLIC_FULL, cnt, row, 8);
                     const int rstart = __shfl_sync(FSLIC_FULL, rs, row, 8);
@@ -393,13 +395,6 @@ __global__ void __launch_bounds__(AS_THREADS, 2) k_assign_warp(AssignParams ap, 
             }
         }
         __syncwarp();
-        if (UPDATE) {
-            // constant feature rows of the MMA A operand: 1 (count), row index 0..3, lane index (data rows per tile)
-            *reinterpret_cast<uint4*>(&s_feat[lane][0]) =
-                make_uint4(0x01010101u, 0x03020100u, (uint32_t)lane * 0x01010101u, 0u);
-            *reinterpret_cast<uint2*>(&s_feat[lane][6]) = make_uint2(0u, 0u);
-        }
-
         // ---- the 4 tiles, one after the other ----
 #pragma unroll 1
         for (int tq = 0; tq < tps; tq++) {
@@ -452,7 +447,9 @@ __global__ void __launch_bounds__(AS_THREADS, 2) k_assign_warp(AssignParams ap, 
             }
 
             // ---- 3. labels ----
-            uint32_t rw = 0;  // local rank bytes of this lane's R pixels (0xFF = contributes to no candidate)
+            uint32_t rw[AS_RG];  // local rank bytes, 4 rows per word (0xFF = contributes to no candidate)
+#pragma unroll
+            for (int gq = 0; gq < AS_RG; gq++) rw[gq] = 0;
 #pragma unroll
             for (int rr = 0; rr < R; rr++) {
                 const bool ok = colok && rr < nrow;
@@ -470,39 +467,66 @@ __global__ void __launch_bounds__(AS_THREADS, 2) k_assign_warp(AssignParams ap, 
                         if (old != 0xFFFF) acc_add_pixel(ac, old, i, j, q[rr]);
                     }
                 }
-                rw |= rb << (8 * rr);
+                rw[rr >> 2] |= rb << (8 * (rr & 3));
             }
 
             // ---- 4. update sums on the tensor cores ----
             if (UPDATE) {
-                // transpose this lane's 4 quads into per-channel words (byte rr = row rr)
-                const uint32_t lo01 = __byte_perm(q[0], q[1], 0x5140), lo23 = __byte_perm(q[2], q[3], 0x5140);
-                const uint32_t hi01 = __byte_perm(q[0], q[1], 0x0062), hi23 = __byte_perm(q[2], q[3], 0x0062);
-                s_feat[lane][3] = __byte_perm(lo01, lo23, 0x5410);  // L
-                *reinterpret_cast<uint2*>(&s_feat[lane][4]) =
-                    make_uint2(__byte_perm(lo01, lo23, 0x7632), __byte_perm(hi01, hi23, 0x5410));  // a, b
-                __syncwarp();
-                for (int nt = 0; nt * 8 < n; nt++) {
-                    // D[feature][candidate] += A[feature][pixel] * B[pixel][candidate];  rows 8..15 of A are zero
+                // only the candidates that actually won a pixel of this tile take part (typically 3-5 of ~9):
+                // compact their ranks so one 8-wide N tile almost always suffices
+                uint32_t mymask = 0;
+#pragma unroll
+                for (int rr = 0; rr < R; rr++) {
+                    const uint32_t rb = (rw[rr >> 2] >> (8 * (rr & 3))) & 0xff;
+                    mymask |= (rb < 32) ? (1u << rb) : 0u;
+                }
+                const uint32_t used = __reduce_or_sync(FSLIC_FULL, mymask);
+                const int nw = __popc(used);
+                uint32_t cw[AS_RG];  // compact winner index per pixel (0xFF = none)
+#pragma unroll
+                for (int gq = 0; gq < AS_RG; gq++) cw[gq] = 0;
+#pragma unroll
+                for (int rr = 0; rr < R; rr++) {
+                    const uint32_t rb = (rw[rr >> 2] >> (8 * (rr & 3))) & 0xff;
+                    const uint32_t ci = (rb < 32) ? (uint32_t)__popc(used & ((1u << rb) - 1u)) : 0xffu;
+                    cw[rr >> 2] |= ci << (8 * (rr & 3));
+                }
+                // cluster index by compact winner index (scratch: the ranked-away cyx array of this warp)
+                if ((used >> lane) & 1u) s_ucyx[0][__popc(used & ((1u << lane) - 1u))] = (int32_t)s_k[tq][lane];
+                for (int nt = 0; nt * 8 < nw; nt++) {
+                    // D[feature][winner] += A[feature][pixel] * B[pixel][winner];  rows 8..15 of A are zero
                     int d[4] = {0, 0, 0, 0};
                     const uint32_t mg = (uint32_t)(nt * 8 + g) * 0x01010101u;
 #pragma unroll
-                    for (int s4 = 0; s4 < 4; s4++) {
-                        const uint32_t w0 = __shfl_sync(FSLIC_FULL, rw, 8 * s4 + tig);
-                        const uint32_t w1 = __shfl_sync(FSLIC_FULL, rw, 8 * s4 + 4 + tig);
-                        const uint32_t a0 = s_feat[8 * s4 + tig][g];
-                        const uint32_t a2 = s_feat[8 * s4 + 4 + tig][g];
-                        mma_u8_16x8x32(d, a0, 0u, a2, 0u, eq80(w0, mg), eq80(w1, mg));
+                    for (int gq = 0; gq < AS_RG; gq++) {
+                        // stage this row group's features: [count 1, row index, lane index, L, a, b, 0, 0] per pixel lane
+                        const uint32_t q0 = q[4 * gq], q1 = q[4 * gq + 1], q2 = q[4 * gq + 2], q3 = q[4 * gq + 3];
+                        const uint32_t lo01 = __byte_perm(q0, q1, 0x5140), lo23 = __byte_perm(q2, q3, 0x5140);
+                        const uint32_t hi01 = __byte_perm(q0, q1, 0x0062), hi23 = __byte_perm(q2, q3, 0x0062);
+                        __syncwarp();  // the previous group's fragments have been read
+                        *reinterpret_cast<uint4*>(&s_feat[lane][0]) =
+                            make_uint4(0x01010101u, 0x03020100u + 0x04040404u * gq, (uint32_t)lane * 0x01010101u,
+                                       __byte_perm(lo01, lo23, 0x5410));
+                        *reinterpret_cast<uint4*>(&s_feat[lane][4]) =
+                            make_uint4(__byte_perm(lo01, lo23, 0x7632), __byte_perm(hi01, hi23, 0x5410), 0u, 0u);
+                        __syncwarp();
+#pragma unroll
+                        for (int s4 = 0; s4 < 4; s4++) {
+                            const uint32_t w0 = __shfl_sync(FSLIC_FULL, cw[gq], 8 * s4 + tig);
+                            const uint32_t w1 = __shfl_sync(FSLIC_FULL, cw[gq], 8 * s4 + 4 + tig);
+                            mma_u8_16x8x32(d, s_feat[8 * s4 + tig][g], 0u, s_feat[8 * s4 + 4 + tig][g], 0u, eq80(w0, mg),
+                                           eq80(w1, mg));
+                        }
                     }
-                    // lane (g, tig): feature g of candidates nt*8 + 2*tig (d0) and +1 (d1), scaled by 128.
+                    // lane (g, tig): feature g of winners nt*8 + 2*tig (d0) and +1 (d1), scaled by 128.
                     //   features: 0 n | 1 sum(row idx) | 2 sum(lane idx) | 3 sum L | 4 sum a | 5 sum b
 #pragma unroll
                     for (int hh = 0; hh < 2; hh++) {
                         const int c = nt * 8 + 2 * tig + hh;
                         const uint32_t v = (uint32_t)d[hh] >> 7;
-                        const uint32_t partner = __shfl_down_sync(FSLIC_FULL, v, 4);  // feature g+1, same candidate
-                        const uint32_t cnt = __shfl_sync(FSLIC_FULL, v, tig);        // feature 0, same candidate
-                        if (c < n && cnt > 0 && g < 6 && (g & 1) == 0) {
+                        const uint32_t partner = __shfl_down_sync(FSLIC_FULL, v, 4);  // feature g+1, same winner
+                        const uint32_t cnt = __shfl_sync(FSLIC_FULL, v, tig);        // feature 0, same winner
+                        if (c < nw && g < 6 && (g & 1) == 0) {
                             unsigned long long word;
                             if (g == 0)
                                 word = (unsigned long long)cnt |
@@ -511,7 +535,7 @@ __global__ void __launch_bounds__(AS_THREADS, 2) k_assign_warp(AssignParams ap, 
                                 word = (unsigned long long)(cnt * (uint32_t)wj0 + v) | ((unsigned long long)partner << 32);
                             else
                                 word = (unsigned long long)v | ((unsigned long long)partner << 32);
-                            atomicAdd(&ac[(int)s_k[tq][c] * 4 + (g >> 1)], word);
+                            atomicAdd(&ac[s_ucyx[0][c] * 4 + (g >> 1)], word);
                         }
                     }
                 }

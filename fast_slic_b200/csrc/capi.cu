@@ -4,6 +4,7 @@
 // the Cython glue that drives it (cfast_slic.pyx:124-197): owns the scratch buffers, sequences the
 // kernels on one stream, never touches the CPU for the data path.
 #include <math.h>
+#include <stdlib.h>
 #include <new>
 #include <string>
 #include <vector>
@@ -598,8 +599,9 @@ extern "C" int fslic_b200_iterate_host(fslic_ctx* c, const uint8_t* h_images, fs
     // streams, so for batches the PCIe copies hide behind the kernels (and vice versa).  With pinned host
     // buffers the copies are truly asynchronous; pageable buffers still work, just without overlap.
     const size_t N = (size_t)c->N;
-    int chunk = batch <= 4 ? batch : (batch + 3) / 4;
-    if (chunk > 16) chunk = 16;
+    // chunks of 32: smaller chunks would pay the fixed latencies of the pipeline (notably the sequential
+    // std::partial_sort replay of ambiguous images) once per chunk, which costs more than the overlap wins
+    const int chunk = batch < 32 ? batch : 32;
     const int nchunks = (batch + chunk - 1) / chunk;
     while ((int)c->pipe_ev.size() < 2 * nchunks) {
         cudaEvent_t e;
@@ -608,6 +610,13 @@ extern "C" int fslic_b200_iterate_host(fslic_ctx* c, const uint8_t* h_images, fs
     }
     fslic_params pp = *p;
     if (nchunks > 1) pp.collect_timing = 0;  // per-stage timings are only meaningful for an unchunked run
+    const bool trace = getenv("FSLIC_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    if (trace) {
+        tev.resize(1 + 4 * nchunks);
+        for (auto& e : tev) cudaEventCreate(&e);
+        cudaEventRecord(tev[0], c->in_stream);
+    }
     for (int k = 0; k < nchunks; k++) {
         const int b0 = k * chunk, nb = (batch - b0 < chunk) ? (batch - b0) : chunk;
         CK(cudaMemcpyAsync(c->d_img + (size_t)b0 * N * 3, h_images + (size_t)b0 * N * 3, (size_t)nb * N * 3,
@@ -615,18 +624,35 @@ extern "C" int fslic_b200_iterate_host(fslic_ctx* c, const uint8_t* h_images, fs
         CK(cudaMemcpyAsync(c->d_cl + (size_t)b0 * c->K, h_clusters + (size_t)b0 * c->K,
                            (size_t)nb * c->K * sizeof(fslic_cluster), cudaMemcpyHostToDevice, c->in_stream));
         CK(cudaEventRecord(c->pipe_ev[2 * k], c->in_stream));
+        if (trace) cudaEventRecord(tev[1 + 4 * k], c->in_stream);
         CK(cudaStreamWaitEvent(c->own_stream, c->pipe_ev[2 * k], 0));
+        if (trace) cudaEventRecord(tev[2 + 4 * k], c->own_stream);
         rc = fslic_b200_iterate(c, c->d_img + (size_t)b0 * N * 3, c->d_cl + (size_t)b0 * c->K, c->d_lab + (size_t)b0 * N, nb,
                                 &pp, c->own_stream);
         if (rc) return rc;
         CK(cudaEventRecord(c->pipe_ev[2 * k + 1], c->own_stream));
+        if (trace) cudaEventRecord(tev[3 + 4 * k], c->own_stream);
         CK(cudaStreamWaitEvent(c->out_stream, c->pipe_ev[2 * k + 1], 0));
         CK(cudaMemcpyAsync(h_labels + (size_t)b0 * N, c->d_lab + (size_t)b0 * N, (size_t)nb * N * 2, cudaMemcpyDeviceToHost,
                            c->out_stream));
         CK(cudaMemcpyAsync(h_clusters + (size_t)b0 * c->K, c->d_cl + (size_t)b0 * c->K,
                            (size_t)nb * c->K * sizeof(fslic_cluster), cudaMemcpyDeviceToHost, c->out_stream));
+        if (trace) cudaEventRecord(tev[4 + 4 * k], c->out_stream);
     }
     CK(cudaStreamSynchronize(c->out_stream));
     CK(cudaStreamSynchronize(c->own_stream));
+    if (trace) {
+        float ms;
+        for (int k = 0; k < nchunks; k++) {
+            float a, b2, c2, d2;
+            cudaEventElapsedTime(&a, tev[0], tev[1 + 4 * k]);
+            cudaEventElapsedTime(&b2, tev[0], tev[2 + 4 * k]);
+            cudaEventElapsedTime(&c2, tev[0], tev[3 + 4 * k]);
+            cudaEventElapsedTime(&d2, tev[0], tev[4 + 4 * k]);
+            fprintf(stderr, "[fslic trace] chunk %d: h2d done %.3f | compute %.3f..%.3f | d2h done %.3f ms\n", k, a, b2, c2, d2);
+        }
+        (void)ms;
+        for (auto e : tev) cudaEventDestroy(e);
+    }
     return FSLIC_OK;
 }

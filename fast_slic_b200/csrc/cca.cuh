@@ -574,50 +574,38 @@ __device__ __forceinline__ void heap_select_body(const uint32_t* __restrict__ ar
             int qpos = consumed, next_lane = 0, nops = 0;
             const int depth = 32 - __clz(K);  // levels of the heap: no sift-down takes more half-steps
             int idle = depth;                 // half-steps since the last issue (start: pipeline empty)
+            const uint32_t q_saddr = (uint32_t)__cvta_generic_to_shared(s_queue);
+            // branch-free: idle lanes read a harmless slot and store nothing
             auto level_step = [&]() {
-                if (act) {
-                    const int l = 2 * hole + 1;
-                    bool done = l >= K;
-                    if (!done) {
-                        uint32_t lo0, hi0, lo1, hi1;
-                        heap.pair(l + 1, lo0, hi0, lo1, hi1);
-                        const bool take_left = (l + 1 >= K) || (hi1 > hi0);  // right unless area[right] > area[left]
-                        const uint32_t clo = take_left ? lo0 : lo1, chi = take_left ? hi0 : hi1;
-                        if (chi > vhi) {
-                            done = true;
-                        } else {
-                            heap.put(hole + 1, clo, chi);
-                            hole = take_left ? l : l + 1;
-                        }
-                    }
-                    if (done) {
-                        heap.put(hole + 1, vlo, vhi);
-                        act = false;
-                    }
-                }
+                const int l = 2 * hole + 1;
+                const bool inb = act && (l < K);
+                uint32_t lo0, hi0, lo1, hi1;
+                heap.pair(inb ? l + 1 : 2, lo0, hi0, lo1, hi1);
+                const bool take_left = (l + 1 >= K) || (hi1 > hi0);  // right unless area[right] > area[left]
+                const uint32_t clo = take_left ? lo0 : lo1, chi = take_left ? hi0 : hi1;
+                const bool move = inb && !(chi > vhi);  // the child moves up, the hole moves down
+                if (act) heap.put(hole + 1, move ? clo : vlo, move ? chi : vhi);  // else: the value lands here
+                hole = move ? (take_left ? l : l + 1) : hole;
+                act = move;
                 __syncwarp();
             };
             while (qpos < qn || idle < depth) {
-                // ---- issue: the next queue element that beats the root (which its predecessors no longer touch) ----
+                // ---- issue: the next queue element, if it beats the root (its predecessors no longer touch it) ----
                 if (qpos < qn) {
+                    uint32_t elo, ehi;
+                    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(elo), "=r"(ehi) : "r"(q_saddr + 8u * (uint32_t)qpos));
                     const uint32_t root_area = hs_area(heap.get(1));
-                    int tries = 0;
-                    while (qpos < qn && tries < 16) {
-                        const unsigned long long e = s_queue[qpos];
-                        qpos++;
-                        tries++;
-                        if (hs_area(e) > root_area) {  // comp(i, first): __pop_heap(first, middle, i)
-                            if (lane == next_lane) {
-                                act = true;
-                                hole = 0;
-                                vlo = (uint32_t)e;
-                                vhi = (uint32_t)(e >> 32);
-                            }
-                            next_lane = (next_lane + 1) & 31;
-                            nops++;
-                            idle = 0;
-                            break;
+                    qpos++;
+                    if (ehi > root_area) {  // comp(i, first): __pop_heap(first, middle, i)
+                        if (lane == next_lane) {
+                            act = true;
+                            hole = 0;
+                            vlo = elo;
+                            vhi = ehi;
                         }
+                        next_lane = (next_lane + 1) & 31;
+                        nops++;
+                        idle = 0;
                     }
                 }
                 // ---- two levels for every sift-down in flight ----
