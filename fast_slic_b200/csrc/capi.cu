@@ -276,7 +276,7 @@ static int run_cca(fslic_ctx* c, const uint16_t* d_in, uint16_t* d_out, int batc
         CK(cudaMemsetAsync(c->counters, 0, sizeof(CcaCounters) * nb, st));
         dim3 g(cp.nblk, nb);
         dim3 gt(ceil_div(c->W, CCL_T), ceil_div(c->H, CCL_T), nb);
-        k_ccl_tile<<<gt, CCL_T * CCL_T, 0, st>>>(cp, in, c->par, c->aux);
+        k_ccl_tile<<<gt, 256, 0, st>>>(cp, in, c->par, c->aux);
         {
             const int seam_px = ((c->W - 1) / CCL_T) * c->H + ((c->H - 1) / CCL_T) * c->W;
             if (seam_px > 0) {
@@ -284,7 +284,7 @@ static int run_cca(fslic_ctx* c, const uint16_t* d_in, uint16_t* d_out, int batc
                 k_ccl_seams<<<gs, 256, 0, st>>>(cp, in, c->par);
             }
         }
-        k_ccl_flatten<<<g, CCA_BLOCK, 0, st>>>(cp, in, c->par, c->aux, c->blkcnt);
+        k_ccl_flatten<<<g, 256, 0, st>>>(cp, in, c->par, c->aux, c->blkcnt);
         k_scan_blocks<<<nb, 1024, 0, st>>>(c->blkcnt, c->blkoff, cp.nblk, cp.nblk, nullptr, 0, 1,
                                            &c->counters[0].ncomp, (int)(sizeof(CcaCounters) / sizeof(int)));
         k_ccl_number<<<g, CCA_BLOCK, 0, st>>>(cp, c->par, c->aux, c->blkoff, c->cleader, c->carea, c->counters);

@@ -99,41 +99,58 @@ __device__ __forceinline__ void ccl_union_s(int* par, int a, int b) {
     }
 }
 
-__global__ void __launch_bounds__(CCL_T * CCL_T) k_ccl_tile(CcaParams cp, const uint16_t* __restrict__ labels,
-                                                             int* __restrict__ par_all,
-                                                             uint32_t* __restrict__ area_all) {
+__global__ void __launch_bounds__(256) k_ccl_tile(CcaParams cp, const uint16_t* __restrict__ labels,
+                                                   int* __restrict__ par_all, uint32_t* __restrict__ area_all) {
+    // 256 threads per 32 x 32 tile: warp w owns rows w, w+8, w+16, w+24 (more CTAs in flight per SM than one
+    // 1024-thread CTA per tile, which made this kernel latency bound)
     __shared__ uint32_t s_lab[CCL_T][CCL_T + 1];
     __shared__ int s_par[CCL_T * CCL_T];
     const int b = blockIdx.z;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int j = blockIdx.x * CCL_T + tx, i = blockIdx.y * CCL_T + ty;
-    const bool ok = (i < cp.H) && (j < cp.W);
-    const int p = i * cp.W + j;
-    // invalid pixels get labels that differ from everything (and from each other along a row / column)
-    const uint32_t v = ok ? (uint32_t)labels[(size_t)b * cp.N + p] : (0x10000u + (uint32_t)threadIdx.x);
-    s_lab[ty][tx] = v;
-    const uint32_t left = __shfl_up_sync(FSLIC_FULL, v, 1);
-    const bool start = (tx == 0) || (v != left);
-    const unsigned m = __ballot_sync(FSLIC_FULL, start);
-    const int sl = 31 - __clz(m & (0xffffffffu >> (31 - tx)));
-    const int me = ty * CCL_T + tx;
-    s_par[me] = ty * CCL_T + sl;
+    const int tx = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int j = blockIdx.x * CCL_T + tx;
+    uint32_t v[4], left[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int ty = w + 8 * r, i = blockIdx.y * CCL_T + ty;
+        const bool ok = (i < cp.H) && (j < cp.W);
+        // invalid pixels get labels that differ from everything (and from each other along a row / column)
+        v[r] = ok ? (uint32_t)labels[(size_t)b * cp.N + (size_t)i * cp.W + j] : (0x10000u + (uint32_t)(ty * CCL_T + tx));
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int ty = w + 8 * r;
+        s_lab[ty][tx] = v[r];
+        left[r] = __shfl_up_sync(FSLIC_FULL, v[r], 1);
+        const bool start = (tx == 0) || (v[r] != left[r]);
+        const unsigned m = __ballot_sync(FSLIC_FULL, start);
+        const int sl = 31 - __clz(m & (0xffffffffu >> (31 - tx)));
+        s_par[ty * CCL_T + tx] = ty * CCL_T + sl;
+    }
     __syncthreads();
-    if (ty > 0) {
-        const uint32_t up = s_lab[ty - 1][tx];
-        if (up == v) {
-            // (me, up) is implied by the pair one pixel to the left when both runs extend there
-            bool need = (tx == 0) || (left != v);
-            if (!need) need = s_lab[ty - 1][tx - 1] != up;
-            if (need) ccl_union_s(s_par, me - CCL_T, me);
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int ty = w + 8 * r, me = ty * CCL_T + tx;
+        if (ty > 0) {
+            const uint32_t up = s_lab[ty - 1][tx];
+            if (up == v[r]) {
+                // (me, up) is implied by the pair one pixel to the left when both runs extend there
+                bool need = (tx == 0) || (left[r] != v[r]);
+                if (!need) need = s_lab[ty - 1][tx - 1] != up;
+                if (need) ccl_union_s(s_par, me - CCL_T, me);
+            }
         }
     }
     __syncthreads();
-    if (ok) {
-        const int r = ccl_find_s(s_par, me);
-        const int ri = blockIdx.y * CCL_T + (r >> 5), rj = blockIdx.x * CCL_T + (r & 31);
-        par_all[(size_t)b * cp.N + p] = ri * cp.W + rj;
-        area_all[(size_t)b * cp.N + p] = 0;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int ty = w + 8 * r, i = blockIdx.y * CCL_T + ty;
+        if (i < cp.H && j < cp.W) {
+            const int root = ccl_find_s(s_par, ty * CCL_T + tx);
+            const int ri = blockIdx.y * CCL_T + (root >> 5), rj = blockIdx.x * CCL_T + (root & 31);
+            const size_t p = (size_t)b * cp.N + (size_t)i * cp.W + j;
+            par_all[p] = ri * cp.W + rj;
+            area_all[p] = 0;
+        }
     }
 }
 
@@ -168,42 +185,53 @@ __global__ void __launch_bounds__(256) k_ccl_seams(CcaParams cp, const uint16_t*
     }
 }
 
-__global__ void __launch_bounds__(CCA_BLOCK) k_ccl_flatten(CcaParams cp, const uint16_t* __restrict__ labels,
-                                                           int* __restrict__ par_all,
-                                                           uint32_t* __restrict__ area_all,
-                                                           int* __restrict__ blkcnt) {
+// Block = 1024 consecutive pixels handled by 256 threads: warp w owns the four 32-pixel chunks 4w .. 4w+3
+// (four independent root chases in flight per lane).
+__global__ void __launch_bounds__(256) k_ccl_flatten(CcaParams cp, const uint16_t* __restrict__ labels,
+                                                     int* __restrict__ par_all, uint32_t* __restrict__ area_all,
+                                                     int* __restrict__ blkcnt) {
     __shared__ int s_cnt;
     const int b = blockIdx.y;
-    const int p = blockIdx.x * CCA_BLOCK + threadIdx.x;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
     const uint16_t* lab = labels + (size_t)b * cp.N;
     int* par = par_all + (size_t)b * cp.N;
-    const bool ok = p < cp.N;
-    const uint32_t v = ok ? lab[p] : 0x10000u;
-    const uint32_t left = __shfl_up_sync(FSLIC_FULL, v, 1);
-    const int j = ok ? (p % cp.W) : 0;
-    const bool start = (lane == 0) || (j == 0) || (v != left);
-    const unsigned m = __ballot_sync(FSLIC_FULL, start);
-    const int s = 31 - __clz(m & (0xffffffffu >> (31 - lane)));
-    int root = 0;
-    if (ok && start) root = ccl_find(par, p);
-    root = __shfl_sync(FSLIC_FULL, root, s);
-    bool isroot = false;
-    if (ok) {
-        par[p] = root;
-        if (start) {
-            // run length: distance to the next run start (or the end of the chunk / image)
-            const unsigned above = (lane == 31) ? 0u : (m >> (lane + 1));
-            int len = above ? (__ffs(above)) : (32 - lane);
-            if (p + len > cp.N) len = cp.N - p;
-            atomicAdd(&area_all[(size_t)b * cp.N + root], (uint32_t)len);
-            isroot = (root == p);
-        }
+    int p[4], sl[4], root[4];
+    unsigned m[4];
+    bool ok[4], start[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        p[r] = blockIdx.x * CCA_BLOCK + (w * 4 + r) * 32 + lane;
+        ok[r] = p[r] < cp.N;
+        const uint32_t v = ok[r] ? lab[p[r]] : 0x10000u;
+        const uint32_t left = __shfl_up_sync(FSLIC_FULL, v, 1);
+        const int j = ok[r] ? (p[r] % cp.W) : 0;
+        start[r] = (lane == 0) || (j == 0) || (v != left);
+        m[r] = __ballot_sync(FSLIC_FULL, start[r]);
+        sl[r] = 31 - __clz(m[r] & (0xffffffffu >> (31 - lane)));
     }
-    const unsigned rm = __ballot_sync(FSLIC_FULL, isroot);
-    if (lane == 0 && rm) atomicAdd(&s_cnt, __popc(rm));
+#pragma unroll
+    for (int r = 0; r < 4; r++) root[r] = (ok[r] && start[r]) ? ccl_find(par, p[r]) : 0;
+    int nroots = 0;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int rt = __shfl_sync(FSLIC_FULL, root[r], sl[r]);
+        bool isroot = false;
+        if (ok[r]) {
+            par[p[r]] = rt;
+            if (start[r]) {
+                // run length: distance to the next run start (or the end of the chunk / image)
+                const unsigned above = (lane == 31) ? 0u : (m[r] >> (lane + 1));
+                int len = above ? (__ffs(above)) : (32 - lane);
+                if (p[r] + len > cp.N) len = cp.N - p[r];
+                atomicAdd(&area_all[(size_t)b * cp.N + rt], (uint32_t)len);
+                isroot = (rt == p[r]);
+            }
+        }
+        nroots += __popc(__ballot_sync(FSLIC_FULL, isroot));
+    }
+    if (lane == 0 && nroots) atomicAdd(&s_cnt, nroots);
     __syncthreads();
     if (threadIdx.x == 0) blkcnt[(size_t)b * cp.nblk + blockIdx.x] = s_cnt;
 }
@@ -339,23 +367,28 @@ __global__ void __launch_bounds__(1024) k_cca_threshold(CcaParams cp, const uint
         for (int t = tid; t < 2048; t += 1024) s_hist[t] = 0;
         __syncthreads();
         const unsigned prefix = s_prefix;
-        for (int base = 0; base < ncomp; base += 1024) {
-            const int c = base + tid;
-            bool act = false;
-            unsigned bin = 0;
-            if (c < ncomp) {
-                const uint32_t a = area[c];
-                act = ((int)a >= cp.thres) && ((pass == first_pass) || ((a >> (shift + 11)) == prefix));
-                bin = (a >> shift) & 2047u;
+        for (int base = 0; base < ncomp; base += 4096) {
+            uint32_t av[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {  // four independent loads in flight per thread
+                const int c = base + u * 1024 + tid;
+                av[u] = (c < ncomp) ? area[c] : 0xffffffffu;
             }
-            // skew-aware histogram: the lanes that share the first active lane's bin add once
-            unsigned am = __ballot_sync(FSLIC_FULL, act);
-            if (am) {
-                const int src = __ffs(am) - 1;
-                const unsigned b0 = __shfl_sync(FSLIC_FULL, bin, src);
-                const unsigned same = __ballot_sync(FSLIC_FULL, act && bin == b0);
-                if (lane == src) atomicAdd(&s_hist[b0], __popc(same));
-                if (act && bin != b0) atomicAdd(&s_hist[bin], 1u);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t a = av[u];
+                const bool valid = a != 0xffffffffu;
+                const bool act = valid && ((int)a >= cp.thres) && ((pass == first_pass) || ((a >> (shift + 11)) == prefix));
+                const unsigned bin = (a >> shift) & 2047u;
+                // skew-aware histogram: the lanes that share the first active lane's bin add once
+                const unsigned am = __ballot_sync(FSLIC_FULL, act);
+                if (am) {
+                    const int src = __ffs(am) - 1;
+                    const unsigned b0 = __shfl_sync(FSLIC_FULL, bin, src);
+                    const unsigned same = __ballot_sync(FSLIC_FULL, act && bin == b0);
+                    if (lane == src) atomicAdd(&s_hist[b0], __popc(same));
+                    if (act && bin != b0) atomicAdd(&s_hist[bin], 1u);
+                }
             }
         }
         __syncthreads();
