@@ -622,12 +622,20 @@ __device__ __forceinline__ void heap_select_body(const uint32_t* __restrict__ ar
                 act = move;
                 __syncwarp();
             };
+            // Software pipelined: the root and the next queue element are fetched right after the first half-step
+            // (by then the sift-down issued at the end of the previous iteration has rewritten the root for good)
+            // and their latency hides behind the second half-step; the issue decision comes last.
             while (qpos < qn || idle < depth) {
-                // ---- issue: the next queue element, if it beats the root (its predecessors no longer touch it) ----
-                if (qpos < qn) {
-                    uint32_t elo, ehi;
+                level_step();
+                uint32_t elo = 0, ehi = 0, root_area = 0xffffffffu;
+                const bool have = qpos < qn;
+                if (have) {
                     asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(elo), "=r"(ehi) : "r"(q_saddr + 8u * (uint32_t)qpos));
-                    const uint32_t root_area = hs_area(heap.get(1));
+                    root_area = hs_area(heap.get(1));
+                }
+                level_step();
+                idle += 2;
+                if (have) {
                     qpos++;
                     if (ehi > root_area) {  // comp(i, first): __pop_heap(first, middle, i)
                         if (lane == next_lane) {
@@ -641,10 +649,6 @@ __device__ __forceinline__ void heap_select_body(const uint32_t* __restrict__ ar
                         idle = 0;
                     }
                 }
-                // ---- two levels for every sift-down in flight ----
-                level_step();
-                level_step();
-                idle += 2;
             }
             if (lane == 0) {
                 s_min = hs_area(heap.get(1));
