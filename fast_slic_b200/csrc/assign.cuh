@@ -94,15 +94,19 @@ __global__ void __launch_bounds__(1024) k_prepare(PrepParams pp, fslic_cluster* 
         atomicAdd(&s_cnt[cell], 1);
     }
     __syncthreads();
-    // exclusive scan of the cell histogram (ncell <= 16384): serial over chunks of blockDim
+    // exclusive scan of the cell histogram (ncell <= ~16K): every thread owns a run of consecutive cells,
+    // one block-wide scan of the run totals (two barriers in all)
     __shared__ int s_warp[32];
-    __shared__ int s_carry;
-    if (tid == 0) s_carry = 0;
-    __syncthreads();
-    for (int base = 0; base <= pp.ncell; base += nt) {
-        const int c = base + tid;
-        const int v = (c <= pp.ncell) ? s_cnt[c] : 0;
-        int x = v;
+    {
+        const int ncnt = pp.ncell + 1;
+        const int per = (ncnt + nt - 1) / nt;
+        const int c0 = tid * per;
+        int local = 0;
+        for (int u = 0; u < per; u++) {
+            const int c = c0 + u;
+            if (c < ncnt) local += s_cnt[c];
+        }
+        int x = local;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             int y = __shfl_up_sync(FSLIC_FULL, x, o);
@@ -112,24 +116,27 @@ __global__ void __launch_bounds__(1024) k_prepare(PrepParams pp, fslic_cluster* 
         __syncthreads();
         if (tid < 32) {
             int w = (tid < (nt >> 5)) ? s_warp[tid] : 0;
+            int z = w;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                int y = __shfl_up_sync(FSLIC_FULL, w, o);
-                if (tid >= o) w += y;
+                int y = __shfl_up_sync(FSLIC_FULL, z, o);
+                if (tid >= o) z += y;
             }
-            s_warp[tid] = w;
+            s_warp[tid] = z - w;
         }
         __syncthreads();
-        const int woff = (tid >> 5) ? s_warp[(tid >> 5) - 1] : 0;
-        const int excl = s_carry + woff + x - v;
-        __syncthreads();
-        if (c <= pp.ncell) {
-            s_cnt[c] = excl;  // becomes the running fill pointer
-            cs[c] = excl;
+        int run = s_warp[tid >> 5] + x - local;  // exclusive prefix of this thread's first cell
+        for (int u = 0; u < per; u++) {
+            const int c = c0 + u;
+            if (c < ncnt) {
+                const int v = s_cnt[c];
+                s_cnt[c] = run;  // becomes the running fill pointer
+                cs[c] = run;
+                run += v;
+            }
         }
-        if (tid == nt - 1) s_carry = excl + v;
-        __syncthreads();
     }
+    __syncthreads();
     for (int k = tid; k < pp.K; k += nt) {
         const CInfo r = ci[k];
         const int cy = (int16_t)(r.cyx & 0xffff), cx = r.cyx >> 16;

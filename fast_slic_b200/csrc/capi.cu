@@ -58,6 +58,7 @@ struct fslic_ctx {
     int* blkcnt = nullptr;         // [Bc][nblk]
     int* blkoff = nullptr;         // [Bc][nblk]
     CcaCounters* counters = nullptr;  // [Bc]
+    unsigned int* ahist = nullptr;    // [Bc][CCA_HIST] histogram of candidate areas
     unsigned long long* heap = nullptr;  // [Bc][Kheap]
     int heap_K = 0;
     // staging for the host entry points
@@ -118,7 +119,7 @@ extern "C" int fslic_b200_destroy(fslic_ctx* c) {
     cudaSetDevice(c->device);
     void* ptrs[] = {c->d_gamma, c->d_labtbl, c->quad,   c->labels,  c->cinfo,  c->acc,    c->cell_start,
                     c->cinfo_tmp, c->sptable, c->par,  c->aux,    c->cleader, c->carea,
-                    c->cnew,    c->fin,      c->blkcnt, c->blkoff,  c->counters, c->heap, c->d_img,
+                    c->cnew,    c->fin,      c->blkcnt, c->blkoff,  c->counters, c->ahist, c->heap, c->d_img,
                     c->d_cl,    c->d_lab};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -203,6 +204,7 @@ extern "C" int fslic_b200_create(int device, int H, int W, int K, int max_batch,
     CKC(dalloc(&c->blkcnt, bc * nblk));
     CKC(dalloc(&c->blkoff, bc * nblk));
     CKC(dalloc(&c->counters, bc));
+    CKC(dalloc(&c->ahist, bc * CCA_HIST));
     c->heap_K = 65536 + 8;
     CKC(dalloc(&c->heap, bc * (size_t)c->heap_K));
     for (auto& e : c->ev) CKC(cudaEventCreate(&e));
@@ -217,6 +219,7 @@ extern "C" int fslic_b200_create(int device, int H, int W, int K, int max_batch,
                 CKC(cudaFuncSetAttribute(pick_assign(ts, stride, upd != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          c->max_smem_optin - 1024));
     CKC(cudaFuncSetAttribute(k_cca_select, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin - 40 * 1024));
+    CKC(cudaFuncSetAttribute(k_debug_heap_select, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin - 40 * 1024));
     CKC(cudaFuncSetAttribute(k_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
     *out = c;
     return FSLIC_OK;
@@ -274,6 +277,7 @@ static int run_cca(fslic_ctx* c, const uint16_t* d_in, uint16_t* d_out, int batc
         const uint16_t* in = d_in + (size_t)b0 * N;
         uint16_t* out = d_out + (size_t)b0 * N;
         CK(cudaMemsetAsync(c->counters, 0, sizeof(CcaCounters) * nb, st));
+        CK(cudaMemsetAsync(c->ahist, 0, sizeof(unsigned int) * CCA_HIST * nb, st));
         dim3 g(cp.nblk, nb);
         dim3 gt(ceil_div(c->W, CCL_T), ceil_div(c->H, CCL_T), nb);
         k_ccl_tile<<<gt, 256, 0, st>>>(cp, in, c->par, c->aux);
@@ -287,8 +291,8 @@ static int run_cca(fslic_ctx* c, const uint16_t* d_in, uint16_t* d_out, int batc
         k_ccl_flatten<<<g, 256, 0, st>>>(cp, in, c->par, c->aux, c->blkcnt);
         k_scan_blocks<<<nb, 1024, 0, st>>>(c->blkcnt, c->blkoff, cp.nblk, cp.nblk, nullptr, 0, 1,
                                            &c->counters[0].ncomp, (int)(sizeof(CcaCounters) / sizeof(int)));
-        k_ccl_number<<<g, CCA_BLOCK, 0, st>>>(cp, c->par, c->aux, c->blkoff, c->cleader, c->carea, c->counters);
-        k_cca_threshold<<<nb, 1024, 0, st>>>(cp, c->carea, c->counters);
+        k_ccl_number<<<g, CCA_BLOCK, 0, st>>>(cp, c->par, c->aux, c->blkoff, c->cleader, c->carea, c->counters, c->ahist);
+        k_cca_threshold<<<nb, 1024, 0, st>>>(cp, c->carea, c->counters, c->ahist);
         k_cca_select<<<nb, 1024, cp.heap_in_smem ? heap_bytes : 0, st>>>(cp, c->carea, c->counters, c->heap);
         k_kept_count<<<g, CCA_BLOCK, 0, st>>>(cp, c->carea, c->counters, c->blkcnt);
         k_scan_blocks<<<nb, 1024, 0, st>>>(c->blkcnt, c->blkoff, cp.nblk, 0, &c->counters[0].ncomp,
@@ -324,8 +328,10 @@ extern "C" int fslic_b200_debug_heap_select(fslic_ctx* c, const int32_t* d_area,
     if (middle + 2 > c->heap_K || middle < 1 || n < 1) return set_err(FSLIC_EINVAL, "bad n/middle");
     CK(cudaSetDevice(c->device));
     CK(cudaMemsetAsync(d_kept, 0, n, (cudaStream_t)stream));
-    k_debug_heap_select<<<1, 1024, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint32_t*>(d_area), n, middle,
-                                                             d_kept, c->heap);
+    const size_t hb = (size_t)(middle + 2) * 8;
+    const int use_smem = hb <= (size_t)(c->max_smem_optin - 40 * 1024);
+    k_debug_heap_select<<<1, 1024, use_smem ? hb : 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint32_t*>(d_area), n,
+                                                                              middle, d_kept, c->heap, use_smem);
     CK(cudaGetLastError());
     return FSLIC_OK;
 }

@@ -23,6 +23,7 @@
 #include "common.cuh"
 
 #define CCA_BLOCK 1024
+#define CCA_HIST 2052  // per-image histogram of candidate areas: [0..2047] exact, [2048] = larger
 
 struct CcaParams {
     int H, W, N;       // N = H*W
@@ -288,9 +289,12 @@ __global__ void __launch_bounds__(CCA_BLOCK) k_ccl_number(CcaParams cp, const in
                                                           const int* __restrict__ blkoff,
                                                           int* __restrict__ cleader_all,
                                                           uint32_t* __restrict__ carea_all,
-                                                          CcaCounters* __restrict__ counters) {
+                                                          CcaCounters* __restrict__ counters,
+                                                          unsigned int* __restrict__ ahist_all) {
     __shared__ int s_warp[32];
     __shared__ int s_cand;
+    __shared__ unsigned int s_hot[32];  // candidate areas 0..31 (the bulk: specks), flushed once per block
+    if (threadIdx.x < 32) s_hot[threadIdx.x] = 0;
     const int b = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int p = blockIdx.x * CCA_BLOCK + tid;
@@ -320,11 +324,17 @@ __global__ void __launch_bounds__(CCA_BLOCK) k_ccl_number(CcaParams cp, const in
         cleader_all[(size_t)b * cp.N + c] = p;
         carea_all[(size_t)b * cp.N + c] = a;
         cand = (int)a >= cp.thres;
+        if (cand) {
+            // histogram of candidate areas: bins 0..2047 exact, bin 2048 = "2048 or more" (k_cca_threshold)
+            if (a < 32u) atomicAdd(&s_hot[a], 1u);
+            else atomicAdd(&ahist_all[(size_t)b * CCA_HIST + (a < 2048u ? a : 2048u)], 1u);
+        }
     }
     const unsigned cm = __ballot_sync(FSLIC_FULL, cand);
     if (lane == 0 && cm) atomicAdd(&s_cand, __popc(cm));
     __syncthreads();
     if (tid == 0 && s_cand) atomicAdd(&counters[b].ncand, s_cand);
+    if (tid < 32 && s_hot[tid]) atomicAdd(&ahist_all[(size_t)b * CCA_HIST + tid], s_hot[tid]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -339,7 +349,8 @@ __global__ void __launch_bounds__(CCA_BLOCK) k_ccl_number(CcaParams cp, const in
 // One CTA per image, streaming the area array three times (4 B x ncomp, L2 resident).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_cca_threshold(CcaParams cp, const uint32_t* __restrict__ carea_all,
-                                                        CcaCounters* __restrict__ counters) {
+                                                        CcaCounters* __restrict__ counters,
+                                                        const unsigned int* __restrict__ ahist_all) {
     __shared__ unsigned int s_hist[2048];
     __shared__ int s_warp[32];
     __shared__ unsigned int s_prefix, s_rank, s_found_bin, s_found_cnt;
@@ -361,13 +372,23 @@ __global__ void __launch_bounds__(1024) k_cca_threshold(CcaParams cp, const uint
         s_rank = (unsigned)cp.K;  // rank (1-based, from the top) still to locate inside the current prefix bucket
     }
     unsigned last_E = 0;
-    const int first_pass = (cp.N < (1 << 22)) ? 1 : 0;  // areas <= N: the top digit is zero for everything
+    // k_ccl_number already histogrammed the candidate areas below 2048; unless K or more candidates are
+    // larger than that (then: the general 3-digit radix select below) the K-th largest is found in it directly
+    const unsigned int* ahist = ahist_all + (size_t)b * CCA_HIST;
+    const unsigned n_big = ahist[2048];
+    const bool from_hist = n_big < (unsigned)cp.K;
+    int first_pass = (cp.N < (1 << 22)) ? 1 : 0;  // areas <= N: the top digit is zero for everything
+    if (from_hist) {
+        first_pass = 2;
+        if (tid == 0) s_rank = (unsigned)cp.K - n_big;
+        __syncthreads();
+    }
     for (int pass = first_pass; pass < 3; pass++) {
         const int shift = 22 - 11 * pass;
-        for (int t = tid; t < 2048; t += 1024) s_hist[t] = 0;
+        for (int t = tid; t < 2048; t += 1024) s_hist[t] = from_hist ? ahist[t] : 0;
         __syncthreads();
         const unsigned prefix = s_prefix;
-        for (int base = 0; base < ncomp; base += 4096) {
+        for (int base = 0; base < (from_hist ? 0 : ncomp); base += 4096) {
             uint32_t av[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) {  // four independent loads in flight per thread
@@ -692,12 +713,20 @@ __global__ void __launch_bounds__(1024) k_cca_select(CcaParams cp, uint32_t* __r
 
 __global__ void __launch_bounds__(1024) k_debug_heap_select(const uint32_t* __restrict__ area, int n, int middle,
                                                             uint8_t* __restrict__ kept,
-                                                            unsigned long long* __restrict__ heap_global) {
-    HeapMem<false> hm;
-    hm.g = heap_global;
-    hm.s = 0;
+                                                            unsigned long long* __restrict__ heap_global, int use_smem) {
+    extern __shared__ __align__(16) unsigned char sel_smem[];
     __shared__ unsigned long long s_queue[SEL_CHUNK];
-    heap_select_body<false>(area, n, middle, 0, hm, nullptr, kept, s_queue);
+    if (use_smem) {
+        HeapMem<true> hm;
+        hm.g = nullptr;
+        hm.s = (uint32_t)__cvta_generic_to_shared(sel_smem);
+        heap_select_body<true>(area, n, middle, 0, hm, nullptr, kept, s_queue);
+    } else {
+        HeapMem<false> hm;
+        hm.g = heap_global;
+        hm.s = 0;
+        heap_select_body<false>(area, n, middle, 0, hm, nullptr, kept, s_queue);
+    }
 }
 
 __device__ __forceinline__ bool cca_is_kept(uint32_t a, int sel_mode, int keep_thres) {

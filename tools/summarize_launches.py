@@ -1,0 +1,18 @@
+"""python tools/summarize_launches.py launches.csv  -> per-kernel totals of an ncu gpu__time_duration launch list"""
+import collections
+import csv
+import sys
+
+lines = [l for l in open(sys.argv[1]) if not l.startswith("==")]
+agg = collections.defaultdict(lambda: [0, 0.0])
+for row in csv.DictReader(lines):
+    v = float(row["Metric Value"].replace(",", ""))
+    v = v / 1000 if row["Metric Unit"] == "ns" else v * (1000 if row["Metric Unit"] == "ms" else 1)
+    a = agg[row["Kernel Name"].split("(")[0][:44]]
+    a[0] += 1
+    a[1] += v
+tot = sum(v[1] for v in agg.values())
+print("%-46s %5s %10s %9s %6s" % ("kernel", "n", "total_us", "avg_us", "share"))
+for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+    print("%-46s %5d %10.1f %9.1f %5.1f%%" % (k, v[0], v[1], v[1] / v[0], 100 * v[1] / tot))
+print("%-46s %5s %10.1f" % ("TOTAL (serialised, cold cache)", "", tot))
