@@ -270,6 +270,9 @@ __device__ __forceinline__ void mma_u8_16x8x32(int (&d)[4], uint32_t a0, uint32_
 //      per cluster that received pixels.  Integer sums are order independent => exact.
 // HBM per processed pixel: 4 B quad read + 2 B label written.
 // ---------------------------------------------------------------------------------------------
+#ifndef FSLIC_UPDATE_MATCH
+#define FSLIC_UPDATE_MATCH 0  // 0: int8 tensor-core one-hot product; 1: MATCH.ANY + REDUX per row (measured 1.4x slower, kept for comparison)
+#endif
 #define AS_RG 1  // row groups of 4 sub-rows per lane (R = 4 * AS_RG rows per warp tile)
 #define AS_R (4 * AS_RG)
 #define AS_T 4   // warp tiles per super tile
@@ -453,6 +456,47 @@ __global__ void __launch_bounds__(AS_THREADS, 2) k_assign_warp(AssignParams ap, 
                 }
             }
 
+            // ---- 3. labels + update sums (context.cpp:316-327) ----
+#if FSLIC_UPDATE_MATCH
+            // Per row: lanes are grouped by their winning cluster with one MATCH.ANY; each group reduces its packed
+            // sums with two REDUX (every group under its own member mask) and its leader issues 3 RED.64.
+            // Integer sums are order independent => exact.
+#pragma unroll
+            for (int rr = 0; rr < R; rr++) {
+                const bool ok = colok && rr < nrow;
+                const bool covered = ok && ((best[rr] >> 16) < FSLIC_BIGSP);
+                uint32_t kk = 0xFFFFu;  // cluster this pixel contributes to (0xFFFF: none)
+                if (covered) {
+                    kk = s_k[tq][best[rr] & 0xff];
+                    lrow[rr * rowpix] = (uint16_t)kk;
+                } else if (ok) {
+                    const int i = wi0 + rr * stride;
+                    if ((i % ap.cfg_stride) >= ap.fresh_from) {
+                        lrow[rr * rowpix] = 0xFFFF;
+                    } else if (UPDATE) {  // a stale label from an earlier pass still counts (context.cpp:318-319)
+                        kk = lrow[rr * rowpix];
+                    }
+                }
+                if (UPDATE) {
+                    const unsigned grp_mask = __match_any_sync(FSLIC_FULL, kk);
+                    if (kk != 0xFFFFu) {
+                        const uint32_t qv = q[rr];
+                        // w0 = count | lane << 8 | L << 17 ; w1 = a | b << 16   (sums over <= 32 lanes cannot carry)
+                        const uint32_t s0 = __reduce_add_sync(grp_mask, 1u | ((uint32_t)lane << 8) | ((qv & 0xffu) << 17));
+                        const uint32_t s1 = __reduce_add_sync(grp_mask, ((qv >> 8) & 0xffu) | ((qv & 0xff0000u)));
+                        if (lane == __ffs(grp_mask) - 1) {
+                            const uint32_t cnt = s0 & 0xffu, sl = (s0 >> 8) & 0x1ffu, sL = s0 >> 17;
+                            const uint32_t i = (uint32_t)(wi0 + rr * stride);
+                            unsigned long long* a3 = ac + (size_t)kk * 4;
+                            atomicAdd(a3 + 0, (unsigned long long)cnt | ((unsigned long long)(cnt * i) << 32));
+                            atomicAdd(a3 + 1, (unsigned long long)(cnt * (uint32_t)wj0 + sl) | ((unsigned long long)sL << 32));
+                            atomicAdd(a3 + 2, (unsigned long long)(s1 & 0xffffu) | ((unsigned long long)(s1 >> 16) << 32));
+                        }
+                    }
+                }
+            }
+            {
+#else
             // ---- 3. labels ----
             uint32_t rw[AS_RG];  // local rank bytes, 4 rows per word (0xFF = contributes to no candidate)
 #pragma unroll
@@ -548,6 +592,10 @@ __global__ void __launch_bounds__(AS_THREADS, 2) k_assign_warp(AssignParams ap, 
                 }
                 __syncwarp();  // s_feat is rewritten by the next tile
             }
+#endif
+#if FSLIC_UPDATE_MATCH
+            }
+#endif
         }
         __syncwarp();  // the list staging is rewritten by the next super tile
     }
