@@ -218,8 +218,8 @@ extern "C" int fslic_b200_create(int device, int H, int W, int K, int max_batch,
             for (int upd = 0; upd < 2; upd++)
                 CKC(cudaFuncSetAttribute(pick_assign(ts, stride, upd != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          c->max_smem_optin - 1024));
-    CKC(cudaFuncSetAttribute(k_cca_select, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin - 40 * 1024));
-    CKC(cudaFuncSetAttribute(k_debug_heap_select, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin - 40 * 1024));
+    CKC(cudaFuncSetAttribute(k_cca_select, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin - 4 * 1024));
+    CKC(cudaFuncSetAttribute(k_debug_heap_select, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin - 4 * 1024));
     CKC(cudaFuncSetAttribute(k_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
     *out = c;
     return FSLIC_OK;
@@ -269,8 +269,8 @@ static int run_cca(fslic_ctx* c, const uint16_t* d_in, uint16_t* d_out, int batc
     CcaParams cp;
     cp.H = c->H; cp.W = c->W; cp.N = N; cp.K = K; cp.thres = thres;
     cp.nblk = ceil_div(N, CCA_BLOCK);
-    const size_t heap_bytes = (size_t)(K + 2) * 8;
-    cp.heap_in_smem = heap_bytes <= (size_t)(c->max_smem_optin - 40 * 1024);
+    const size_t heap_bytes = (size_t)(2 * K + 4) * 8;  // live slots + the +infinity padding of the replay loop
+    cp.heap_in_smem = heap_bytes + SEL_CHUNK * 8 <= (size_t)(c->max_smem_optin - 8 * 1024);
     if (K + 2 > c->heap_K) return set_err(FSLIC_EINVAL, "K too large for the selection heap");
     for (int b0 = 0; b0 < batch; b0 += c->cca_batch) {
         const int nb = (batch - b0 < c->cca_batch) ? (batch - b0) : c->cca_batch;
@@ -293,7 +293,7 @@ static int run_cca(fslic_ctx* c, const uint16_t* d_in, uint16_t* d_out, int batc
                                            &c->counters[0].ncomp, (int)(sizeof(CcaCounters) / sizeof(int)));
         k_ccl_number<<<g, CCA_BLOCK, 0, st>>>(cp, c->par, c->aux, c->blkoff, c->cleader, c->carea, c->counters, c->ahist);
         k_cca_threshold<<<nb, 1024, 0, st>>>(cp, c->carea, c->counters, c->ahist);
-        k_cca_select<<<nb, 1024, cp.heap_in_smem ? heap_bytes : 0, st>>>(cp, c->carea, c->counters, c->heap);
+        k_cca_select<<<nb, 1024, SEL_CHUNK * 8 + (cp.heap_in_smem ? heap_bytes : 0), st>>>(cp, c->carea, c->counters, c->heap);
         k_kept_count<<<g, CCA_BLOCK, 0, st>>>(cp, c->carea, c->counters, c->blkcnt);
         k_scan_blocks<<<nb, 1024, 0, st>>>(c->blkcnt, c->blkoff, cp.nblk, 0, &c->counters[0].ncomp,
                                            (int)(sizeof(CcaCounters) / sizeof(int)), CCA_BLOCK,
@@ -328,9 +328,9 @@ extern "C" int fslic_b200_debug_heap_select(fslic_ctx* c, const int32_t* d_area,
     if (middle + 2 > c->heap_K || middle < 1 || n < 1) return set_err(FSLIC_EINVAL, "bad n/middle");
     CK(cudaSetDevice(c->device));
     CK(cudaMemsetAsync(d_kept, 0, n, (cudaStream_t)stream));
-    const size_t hb = (size_t)(middle + 2) * 8;
-    const int use_smem = hb <= (size_t)(c->max_smem_optin - 40 * 1024);
-    k_debug_heap_select<<<1, 1024, use_smem ? hb : 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint32_t*>(d_area), n,
+    const size_t hb = (size_t)(2 * middle + 4) * 8;
+    const int use_smem = hb + SEL_CHUNK * 8 <= (size_t)(c->max_smem_optin - 8 * 1024);
+    k_debug_heap_select<<<1, 1024, SEL_CHUNK * 8 + (use_smem ? hb : 0), (cudaStream_t)stream>>>(reinterpret_cast<const uint32_t*>(d_area), n,
                                                                               middle, d_kept, c->heap, use_smem);
     CK(cudaGetLastError());
     return FSLIC_OK;

@@ -477,7 +477,8 @@ __global__ void __launch_bounds__(1024) k_cca_threshold(CcaParams cp, const uint
 //     survivors are compacted IN ORDER into a shared queue;
 //   * thread 0 replays the queue sequentially through __pop_heap / __adjust_heap / __push_heap.
 // ---------------------------------------------------------------------------------------------
-#define SEL_CHUNK 4096  // components examined per round (4 per thread)
+#define SEL_CHUNK 8192  // components examined per round (8 per thread); the queue lives in dynamic shared memory
+#define SEL_PER 8
 
 __device__ __forceinline__ uint32_t hs_area(unsigned long long e) { return (uint32_t)(e >> 32); }
 
@@ -548,25 +549,35 @@ __device__ __forceinline__ void heap_select_body(const uint32_t* __restrict__ ar
     __shared__ int s_qn, s_filled;
     __shared__ uint32_t s_min;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x;
-    const int per = SEL_CHUNK / nt;  // consecutive components per thread
     if (tid == 0) {
         s_filled = 0;
         s_min = 0;
     }
+    if (SMEM)  // +infinity padding behind the K live slots (see the replay loop)
+        for (int u = K + 1 + tid; u < 2 * K + 4; u += nt) heap.put(u, 0u, 0xffffffffu);
     __syncthreads();
+    // thread t owns components base + t*SEL_PER .. +SEL_PER-1 (ascending order inside the thread); the next
+    // chunk is prefetched into registers while warp 0 replays the current one
+    uint32_t cur[SEL_PER], nxt[SEL_PER];
+#pragma unroll
+    for (int u = 0; u < SEL_PER; u++) {
+        const int c = tid * SEL_PER + u;
+        cur[u] = (c < ncomp) ? area[c] : 0u;
+    }
     for (int base = 0; base < ncomp; base += SEL_CHUNK) {
+#pragma unroll
+        for (int u = 0; u < SEL_PER; u++) {
+            const int c = base + SEL_CHUNK + tid * SEL_PER + u;
+            nxt[u] = (c < ncomp) ? area[c] : 0u;
+        }
         const int filled = s_filled;
         const bool filling = filled < K;
         const uint32_t curmin = s_min;
-        // thread t owns components base + t*per .. +per-1 (keeps ascending order inside the thread)
-        unsigned long long mine[SEL_CHUNK / 256];
         int cnt = 0;
-        for (int u = 0; u < per; u++) {
-            const int c = base + tid * per + u;
-            if (c < ncomp) {
-                const uint32_t a = area[c];
-                if ((int)a >= thres && (filling || a > curmin)) mine[cnt++] = ((unsigned long long)a << 32) | (uint32_t)c;
-            }
+#pragma unroll
+        for (int u = 0; u < SEL_PER; u++) {
+            const int c = base + tid * SEL_PER + u;
+            cnt += (c < ncomp) && ((int)cur[u] >= thres) && (filling || cur[u] > curmin);
         }
         // ordered compaction: exclusive scan of cnt over the CTA
         int x = cnt;
@@ -589,8 +600,13 @@ __device__ __forceinline__ void heap_select_body(const uint32_t* __restrict__ ar
             if (lane == 31) s_qn = z;
         }
         __syncthreads();
-        const int pos = s_warp[warp] + x - cnt;
-        for (int u = 0; u < cnt; u++) s_queue[pos + u] = mine[u];
+        int pos = s_warp[warp] + x - cnt;
+#pragma unroll
+        for (int u = 0; u < SEL_PER; u++) {
+            const int c = base + tid * SEL_PER + u;
+            if ((c < ncomp) && ((int)cur[u] >= thres) && (filling || cur[u] > curmin))
+                s_queue[pos++] = ((unsigned long long)cur[u] << 32) | (uint32_t)c;
+        }
         __syncthreads();
         const int qn = s_qn;
         // phase 1: the first K candidates fill the heap array in order
@@ -622,10 +638,70 @@ __device__ __forceinline__ void heap_select_body(const uint32_t* __restrict__ ar
             // Timing is deterministic, so no cross-lane queries are needed: a sift-down moves exactly one
             // level per half-step (or has finished), one new sift-down may be issued per full step (two
             // levels behind its predecessor), and `depth` half-steps after the last issue everything is done.
+            int nops = 0;
+            if (SMEM) {
+                // Shared-memory heap, padded with +infinity slots up to 2K+3 so a node's children can always be
+                // loaded: missing children compare as +infinity, which reproduces libstdc++'s one-child and
+                // leaf cases without any bounds test.  State per lane: shared byte address of its hole.
+                bool act = false;
+                uint32_t haddr = heap.s + 8u, vlo = 0, vhi = 0;
+                int qpos = consumed, next_lane = 0;
+                const int depth = 32 - __clz(K);
+                int idle = depth;
+                const uint32_t q_saddr = (uint32_t)__cvta_generic_to_shared(s_queue);
+                const uint32_t base = heap.s;
+                auto level_step = [&]() {
+                    const uint32_t caddr = 2u * haddr - base;  // slot(h) = h + 1 ; children at slots 2h+2, 2h+3
+                    uint32_t c0lo = 0, c0hi = 0, c1lo = 0, c1hi = 0;
+                    if (act) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                          : "=r"(c0lo), "=r"(c0hi), "=r"(c1lo), "=r"(c1hi) : "r"(caddr));
+                    const bool tl = c1hi > c0hi;  // right unless area[right] > area[left]
+                    const uint32_t clo = tl ? c0lo : c1lo, chi = tl ? c0hi : c1hi;
+                    const bool mv = act && !(chi > vhi);
+                    if (act) asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(haddr), "r"(mv ? clo : vlo), "r"(mv ? chi : vhi) : "memory");
+                    haddr = mv ? (tl ? caddr : caddr + 8u) : haddr;
+                    act = mv;
+                    __syncwarp();
+                };
+                while (qpos < qn || idle < depth) {
+                    level_step();
+                    // every lane looks at one queue element of the window [qpos, qpos+32): elements that do not beat
+                    // the root now never will (the root only grows), so whole windows are skipped at once
+                    uint32_t elo = 0, ehi = 0, root_area = 0xffffffffu;
+                    const bool have = qpos < qn;
+                    if (have) {
+                        if (qpos + lane < qn)
+                            asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(elo), "=r"(ehi) : "r"(q_saddr + 8u * (uint32_t)(qpos + lane)));
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(root_area) : "r"(base + 12u));
+                    }
+                    level_step();
+                    idle += 2;
+                    if (have) {
+                        const unsigned hit = __ballot_sync(FSLIC_FULL, (qpos + lane < qn) && (ehi > root_area));
+                        if (hit == 0) {
+                            qpos += 32;
+                        } else {
+                            const int first = __ffs(hit) - 1;  // comp(i, first): __pop_heap(first, middle, i)
+                            const uint32_t ilo = __shfl_sync(FSLIC_FULL, elo, first);
+                            const uint32_t ihi = __shfl_sync(FSLIC_FULL, ehi, first);
+                            if (lane == next_lane) {
+                                act = true;
+                                haddr = base + 8u;
+                                vlo = ilo;
+                                vhi = ihi;
+                            }
+                            next_lane = (next_lane + 1) & 31;
+                            nops++;
+                            idle = 0;
+                            qpos += first + 1;
+                        }
+                    }
+                }
+            } else {
             bool act = false;
             int hole = 0;
             uint32_t vlo = 0, vhi = 0;
-            int qpos = consumed, next_lane = 0, nops = 0;
+            int qpos = consumed, next_lane = 0;
             const int depth = 32 - __clz(K);  // levels of the heap: no sift-down takes more half-steps
             int idle = depth;                 // half-steps since the last issue (start: pipeline empty)
             const uint32_t q_saddr = (uint32_t)__cvta_generic_to_shared(s_queue);
@@ -671,6 +747,7 @@ __device__ __forceinline__ void heap_select_body(const uint32_t* __restrict__ ar
                     }
                 }
             }
+            }
             if (lane == 0) {
                 s_min = hs_area(heap.get(1));
                 if (dbg_ops) *dbg_ops += nops;
@@ -678,6 +755,8 @@ __device__ __forceinline__ void heap_select_body(const uint32_t* __restrict__ ar
         }
         if (tid == 0) s_filled = f;
         __syncthreads();
+#pragma unroll
+        for (int u = 0; u < SEL_PER; u++) cur[u] = nxt[u];
     }
     // publish the selected set
     const int filled = s_filled;
@@ -691,8 +770,8 @@ __device__ __forceinline__ void heap_select_body(const uint32_t* __restrict__ ar
 __global__ void __launch_bounds__(1024) k_cca_select(CcaParams cp, uint32_t* __restrict__ carea_all,
                                                      CcaCounters* __restrict__ counters,
                                                      unsigned long long* __restrict__ heap_global) {
-    extern __shared__ __align__(16) unsigned char sel_smem[];
-    __shared__ unsigned long long s_queue[SEL_CHUNK];
+    extern __shared__ __align__(16) unsigned char sel_smem[];  // [queue: SEL_CHUNK x u64][heap: (2K+4) x u64 if it fits]
+    unsigned long long* s_queue = reinterpret_cast<unsigned long long*>(sel_smem);
     const int b = blockIdx.x;
     CcaCounters* ct = &counters[b];
     if (!ct->need_sim) return;  // k_cca_threshold settled it (or cca.cpp:225 is not taken)
@@ -700,7 +779,7 @@ __global__ void __launch_bounds__(1024) k_cca_select(CcaParams cp, uint32_t* __r
     if (cp.heap_in_smem) {
         HeapMem<true> hm;
         hm.g = nullptr;
-        hm.s = (uint32_t)__cvta_generic_to_shared(sel_smem);
+        hm.s = (uint32_t)__cvta_generic_to_shared(sel_smem + SEL_CHUNK * 8);
         heap_select_body<true>(area, ct->ncomp, cp.K, cp.thres, hm, area, nullptr, s_queue, &ct->dbg_ops);
     } else {
         HeapMem<false> hm;
@@ -715,11 +794,11 @@ __global__ void __launch_bounds__(1024) k_debug_heap_select(const uint32_t* __re
                                                             uint8_t* __restrict__ kept,
                                                             unsigned long long* __restrict__ heap_global, int use_smem) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
-    __shared__ unsigned long long s_queue[SEL_CHUNK];
+    unsigned long long* s_queue = reinterpret_cast<unsigned long long*>(sel_smem);
     if (use_smem) {
         HeapMem<true> hm;
         hm.g = nullptr;
-        hm.s = (uint32_t)__cvta_generic_to_shared(sel_smem);
+        hm.s = (uint32_t)__cvta_generic_to_shared(sel_smem + SEL_CHUNK * 8);
         heap_select_body<true>(area, n, middle, 0, hm, nullptr, kept, s_queue);
     } else {
         HeapMem<false> hm;
