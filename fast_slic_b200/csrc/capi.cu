@@ -65,7 +65,8 @@ struct fslic_ctx {
     uint8_t *d_img = nullptr, *h_img = nullptr;
     fslic_cluster *d_cl = nullptr, *h_cl = nullptr;
     uint16_t *d_lab = nullptr, *h_lab = nullptr;
-    cudaStream_t own_stream = nullptr, in_stream = nullptr, out_stream = nullptr;
+    cudaStream_t own_stream = nullptr, in_stream = nullptr, out_stream = nullptr, side_stream = nullptr;
+    cudaEvent_t side_fork = nullptr, side_join = nullptr;
     std::vector<cudaEvent_t> pipe_ev;  // [2 * chunks]: input-ready / compute-done events of iterate_host
     // timing
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -132,6 +133,9 @@ extern "C" int fslic_b200_destroy(fslic_ctx* c) {
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->in_stream) cudaStreamDestroy(c->in_stream);
     if (c->out_stream) cudaStreamDestroy(c->out_stream);
+    if (c->side_stream) cudaStreamDestroy(c->side_stream);
+    if (c->side_fork) cudaEventDestroy(c->side_fork);
+    if (c->side_join) cudaEventDestroy(c->side_join);
     for (auto& e : c->pipe_ev) cudaEventDestroy(e);
     delete c;
     return FSLIC_OK;
@@ -211,6 +215,9 @@ extern "C" int fslic_b200_create(int device, int H, int W, int K, int max_batch,
     CKC(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     CKC(cudaStreamCreateWithFlags(&c->in_stream, cudaStreamNonBlocking));
     CKC(cudaStreamCreateWithFlags(&c->out_stream, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+    CKC(cudaEventCreateWithFlags(&c->side_fork, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&c->side_join, cudaEventDisableTiming));
 
     // opt in to large dynamic shared memory once
     for (int ts : {128, 192, 256, 384})
@@ -267,7 +274,7 @@ static int run_cca(fslic_ctx* c, const uint16_t* d_in, uint16_t* d_out, int batc
                    int* launches) {
     const int N = c->N;
     CcaParams cp;
-    cp.H = c->H; cp.W = c->W; cp.N = N; cp.K = K; cp.thres = thres;
+    cp.H = c->H; cp.W = c->W; cp.N = N; cp.K = K; cp.thres = thres; cp.which = -1;
     cp.nblk = ceil_div(N, CCA_BLOCK);
     const size_t heap_bytes = (size_t)(2 * K + 4) * 8;  // live slots + the +infinity padding of the replay loop
     cp.heap_in_smem = heap_bytes + SEL_CHUNK * 8 <= (size_t)(c->max_smem_optin - 8 * 1024);
@@ -290,23 +297,45 @@ static int run_cca(fslic_ctx* c, const uint16_t* d_in, uint16_t* d_out, int batc
         }
         k_ccl_flatten<<<g, 256, 0, st>>>(cp, in, c->par, c->aux, c->blkcnt);
         k_scan_blocks<<<nb, 1024, 0, st>>>(c->blkcnt, c->blkoff, cp.nblk, cp.nblk, nullptr, 0, 1,
-                                           &c->counters[0].ncomp, (int)(sizeof(CcaCounters) / sizeof(int)));
+                                           &c->counters[0].ncomp, (int)(sizeof(CcaCounters) / sizeof(int)), nullptr, -1);
         k_ccl_number<<<g, CCA_BLOCK, 0, st>>>(cp, c->par, c->aux, c->blkoff, c->cleader, c->carea, c->counters, c->ahist);
         k_cca_threshold<<<nb, 1024, 0, st>>>(cp, c->carea, c->counters, c->ahist);
+        // Everything after the threshold decision depends on the kept set.  For images k_cca_threshold settled
+        // that is known now; for the (few) images whose ties need the sequential std::partial_sort replay it
+        // is known only after k_cca_select, which keeps a handful of SMs busy for ~1 ms.  So for batches the
+        // tail runs twice: for the settled images on a side stream concurrently with the replay, and for the
+        // replayed images afterwards.
+        auto tail = [&](int which, cudaStream_t ts) {
+            CcaParams cq = cp;
+            cq.which = which;
+            k_kept_count<<<g, CCA_BLOCK, 0, ts>>>(cq, c->carea, c->counters, c->blkcnt);
+            k_scan_blocks<<<nb, 1024, 0, ts>>>(c->blkcnt, c->blkoff, cp.nblk, 0, &c->counters[0].ncomp,
+                                               (int)(sizeof(CcaCounters) / sizeof(int)), CCA_BLOCK,
+                                               &c->counters[0].nkept, (int)(sizeof(CcaCounters) / sizeof(int)),
+                                               c->counters, which);
+            k_kept_label<<<g, CCA_BLOCK, 0, ts>>>(cq, c->carea, c->counters, c->blkoff, c->cnew);
+            int ab = ceil_div(N, 256 * 8);
+            if (ab > c->num_sms * 8) ab = c->num_sms * 8;
+            dim3 ga(ab, nb);
+            k_cca_absorb<<<ga, 256, 0, ts>>>(cq, c->par, c->aux, c->cleader, c->cnew, c->counters, c->fin);
+            int ob = ceil_div(N, 256);
+            if (ob > c->num_sms * 32) ob = c->num_sms * 32;
+            dim3 go(ob, nb);
+            k_cca_output<<<go, 256, 0, ts>>>(cq, c->par, c->fin, out, c->counters);
+        };
+        const bool split = nb >= 4;
+        if (split) {
+            CK(cudaEventRecord(c->side_fork, st));
+            CK(cudaStreamWaitEvent(c->side_stream, c->side_fork, 0));
+            tail(0, c->side_stream);
+            CK(cudaEventRecord(c->side_join, c->side_stream));
+        }
         k_cca_select<<<nb, 1024, SEL_CHUNK * 8 + (cp.heap_in_smem ? heap_bytes : 0), st>>>(cp, c->carea, c->counters, c->heap);
-        k_kept_count<<<g, CCA_BLOCK, 0, st>>>(cp, c->carea, c->counters, c->blkcnt);
-        k_scan_blocks<<<nb, 1024, 0, st>>>(c->blkcnt, c->blkoff, cp.nblk, 0, &c->counters[0].ncomp,
-                                           (int)(sizeof(CcaCounters) / sizeof(int)), CCA_BLOCK,
-                                           &c->counters[0].nkept, (int)(sizeof(CcaCounters) / sizeof(int)));
-        k_kept_label<<<g, CCA_BLOCK, 0, st>>>(cp, c->carea, c->counters, c->blkoff, c->cnew);
-        int ab = ceil_div(N, 256 * 8);
-        if (ab > c->num_sms * 8) ab = c->num_sms * 8;
-        dim3 ga(ab, nb);
-        k_cca_absorb<<<ga, 256, 0, st>>>(cp, c->par, c->aux, c->cleader, c->cnew, c->counters, c->fin);
-        int ob = ceil_div(N, 256);
-        if (ob > c->num_sms * 32) ob = c->num_sms * 32;
-        dim3 go(ob, nb);
-        k_cca_output<<<go, 256, 0, st>>>(cp, c->par, c->fin, out);
+        tail(split ? 1 : -1, st);
+        if (split) {
+            CK(cudaStreamWaitEvent(st, c->side_join, 0));
+            if (launches) *launches += 5;
+        }
         CK(cudaGetLastError());
         if (launches) *launches += 12;
     }

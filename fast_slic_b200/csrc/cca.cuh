@@ -31,7 +31,10 @@ struct CcaParams {
     int thres;         // min_threshold
     int nblk;          // ceil(N / CCA_BLOCK)
     int heap_in_smem;  // k_cca_select keeps its heap in shared memory
+    int which;         // post-selection kernels: -1 all images, 0 only images settled by k_cca_threshold, 1 only replayed ones
 };
+
+__device__ __forceinline__ bool cca_skip_image(const CcaParams& cp, const struct CcaCounters* ct);
 
 // Per-image scalar scratch
 struct CcaCounters {
@@ -44,6 +47,10 @@ struct CcaCounters {
     int dbg_ops;   // heap replacements performed by k_cca_select (diagnostics)
     int dbg_t;     // K-th largest candidate area found by k_cca_threshold (diagnostics)
 };
+
+__device__ __forceinline__ bool cca_skip_image(const CcaParams& cp, const CcaCounters* ct) {
+    return cp.which >= 0 && (ct->need_sim != 0) != (cp.which != 0);
+}
 
 __device__ __forceinline__ int ccl_find(const int* par, int x) {
     int p = par[x];
@@ -242,10 +249,12 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(const int* __restrict__ cn
                                                       int stride_per_image, int n_static,
                                                       const int* __restrict__ n_dev_base, int n_dev_stride_ints,
                                                       int n_div, int* __restrict__ total_base,
-                                                      int total_stride_ints) {
+                                                      int total_stride_ints,
+                                                      const CcaCounters* __restrict__ skip_counters, int which) {
     __shared__ int s_warp[32];
     __shared__ int s_carry;
     const int b = blockIdx.x;
+    if (skip_counters && which >= 0 && (skip_counters[b].need_sim != 0) != (which != 0)) return;
     const int tid = threadIdx.x;
     const int* cnt = cnt_all + (size_t)b * stride_per_image;
     int* off = off_all + (size_t)b * stride_per_image;
@@ -817,6 +826,7 @@ __global__ void __launch_bounds__(CCA_BLOCK) k_kept_count(CcaParams cp, const ui
                                                           int* __restrict__ blkcnt) {
     __shared__ int s_cnt;
     const int b = blockIdx.y;
+    if (cca_skip_image(cp, &counters[b])) return;
     const int ncomp = counters[b].ncomp;
     if (blockIdx.x * CCA_BLOCK >= ncomp) return;
     if (threadIdx.x == 0) s_cnt = 0;
@@ -836,6 +846,7 @@ __global__ void __launch_bounds__(CCA_BLOCK) k_kept_label(CcaParams cp, const ui
                                                           uint16_t* __restrict__ cnew_all) {
     __shared__ int s_warp[32];
     const int b = blockIdx.y;
+    if (cca_skip_image(cp, &counters[b])) return;
     const int ncomp = counters[b].ncomp;
     if (blockIdx.x * CCA_BLOCK >= ncomp) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -870,6 +881,7 @@ __global__ void __launch_bounds__(256) k_cca_absorb(CcaParams cp, const int* __r
                                                     const CcaCounters* __restrict__ counters,
                                                     uint16_t* __restrict__ final_all) {
     const int b = blockIdx.y;
+    if (cca_skip_image(cp, &counters[b])) return;
     const int ncomp = counters[b].ncomp;
     const int* par = par_all + (size_t)b * cp.N;
     const uint32_t* aux = aux_all + (size_t)b * cp.N;
@@ -894,8 +906,10 @@ __global__ void __launch_bounds__(256) k_cca_absorb(CcaParams cp, const int* __r
 
 __global__ void __launch_bounds__(256) k_cca_output(CcaParams cp, const int* __restrict__ par_all,
                                                     const uint16_t* __restrict__ final_all,
-                                                    uint16_t* __restrict__ out_all) {
+                                                    uint16_t* __restrict__ out_all,
+                                                    const CcaCounters* __restrict__ counters) {
     const int b = blockIdx.y;
+    if (cca_skip_image(cp, &counters[b])) return;
     const int* par = par_all + (size_t)b * cp.N;
     const uint16_t* fin = final_all + (size_t)b * cp.N;
     uint16_t* out = out_all + (size_t)b * cp.N;
