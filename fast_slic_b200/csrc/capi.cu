@@ -62,9 +62,9 @@ struct fslic_ctx {
     unsigned long long* heap = nullptr;  // [Bc][Kheap]
     int heap_K = 0;
     // staging for the host entry points
-    uint8_t *d_img = nullptr, *h_img = nullptr;
-    fslic_cluster *d_cl = nullptr, *h_cl = nullptr;
-    uint16_t *d_lab = nullptr, *h_lab = nullptr;
+    uint8_t* d_img = nullptr;
+    fslic_cluster* d_cl = nullptr;
+    uint16_t* d_lab = nullptr;
     cudaStream_t own_stream = nullptr, in_stream = nullptr, out_stream = nullptr, side_stream = nullptr;
     cudaEvent_t side_fork = nullptr, side_join = nullptr;
     std::vector<cudaEvent_t> pipe_ev;  // [2 * chunks]: input-ready / compute-done events of iterate_host
@@ -124,9 +124,6 @@ extern "C" int fslic_b200_destroy(fslic_ctx* c) {
                     c->d_cl,    c->d_lab};
     for (void* p : ptrs)
         if (p) cudaFree(p);
-    if (c->h_img) cudaFreeHost(c->h_img);
-    if (c->h_cl) cudaFreeHost(c->h_cl);
-    if (c->h_lab) cudaFreeHost(c->h_lab);
     for (auto& e : c->ev)
         if (e) cudaEventDestroy(e);
     for (auto& e : c->kev) cudaEventDestroy(e);
@@ -197,6 +194,10 @@ extern "C" int fslic_b200_create(int device, int H, int W, int K, int max_batch,
     size_t bc = (12ull << 30) / per_img;
     if (bc < 1) bc = 1;
     if (bc > B) bc = B;
+    if (const char* e = getenv("FSLIC_CCA_BATCH")) {  // test hook: force the sub-batched CCA path
+        const long v = atol(e);
+        if (v >= 1 && (size_t)v < bc) bc = (size_t)v;
+    }
     c->cca_batch = (int)bc;
     const int nblk = ceil_div(c->N, CCA_BLOCK);
     CKC(dalloc(&c->par, bc * N));
@@ -600,9 +601,6 @@ static int ensure_staging(fslic_ctx* c) {
     CK(dalloc(&c->d_img, B * N * 3));
     CK(dalloc(&c->d_cl, B * c->K));
     CK(dalloc(&c->d_lab, B * N));
-    CK(cudaMallocHost(reinterpret_cast<void**>(&c->h_img), B * N * 3));
-    CK(cudaMallocHost(reinterpret_cast<void**>(&c->h_cl), B * c->K * sizeof(fslic_cluster)));
-    CK(cudaMallocHost(reinterpret_cast<void**>(&c->h_lab), B * N * 2));
     return FSLIC_OK;
 }
 
@@ -636,7 +634,11 @@ extern "C" int fslic_b200_iterate_host(fslic_ctx* c, const uint8_t* h_images, fs
     const size_t N = (size_t)c->N;
     // chunks of 32: smaller chunks would pay the fixed latencies of the pipeline (notably the sequential
     // std::partial_sort replay of ambiguous images) once per chunk, which costs more than the overlap wins
-    const int chunk = batch < 32 ? batch : 32;
+    int chunk = batch < 32 ? batch : 32;
+    if (const char* e = getenv("FSLIC_HOST_CHUNK")) {  // test hook: force the multi-chunk pipeline
+        const int v = atoi(e);
+        if (v >= 1 && v < chunk) chunk = v;
+    }
     const int nchunks = (batch + chunk - 1) / chunk;
     while ((int)c->pipe_ev.size() < 2 * nchunks) {
         cudaEvent_t e;

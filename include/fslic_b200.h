@@ -84,8 +84,9 @@ int fslic_b200_iterate(fslic_ctx* ctx, const uint8_t* d_images, fslic_cluster* d
                        int batch, const fslic_params* params, void* stream);
 
 /* The same call as the reference-facing plugin makes it: HOST buffers in, HOST buffers out
- * (what SlicModel.iterate does with a numpy image, cfast_slic.pyx:150-260).  Copies are
- * staged through pinned memory owned by the context; synchronous. */
+ * (what SlicModel.iterate does with a numpy image, cfast_slic.pyx:150-260).  H2D copy, kernels and
+ * D2H copy are pipelined over chunks of 32 images on three streams (pass pinned buffers for true overlap);
+ * returns when the results are in the host buffers. */
 int fslic_b200_iterate_host(fslic_ctx* ctx, const uint8_t* h_images, fslic_cluster* h_clusters, uint16_t* h_labels,
                             int batch, const fslic_params* params);
 int fslic_b200_initialize_clusters_host(fslic_ctx* ctx, const uint8_t* h_images, fslic_cluster* h_clusters,

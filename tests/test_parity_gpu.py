@@ -95,6 +95,26 @@ def test_batch_matches_single(port):
         assert clusters[b].cpu().numpy().tobytes() == cl.tobytes() == clusters_h[b].tobytes()
 
 
+def test_sub_batched_paths(port, monkeypatch):
+    """Forces the CCA sub-batch loop (scratch smaller than the batch) and the multi-chunk host pipeline."""
+    from fast_slic_b200 import Slic, clear_engine_cache
+    monkeypatch.setenv("FSLIC_CCA_BATCH", "2")
+    monkeypatch.setenv("FSLIC_HOST_CHUNK", "3")
+    clear_engine_cache()
+    try:
+        H, W, K, B = 120, 160, 40, 7
+        imgs = np.stack([make_image("noise" if b % 3 == 0 else "syn", H, W, seed=40 + b) for b in range(B)])
+        s = Slic(num_components=K, min_size_factor=0.0)
+        lab_d = s.iterate_batch(torch.from_numpy(imgs).cuda()).cpu().numpy().view(np.uint16)
+        lab_h = s.iterate_batch(imgs).view(np.uint16)
+        for b in range(B):
+            cl = port.initialize(imgs[b], K)
+            want = port.iterate(imgs[b], cl, 10, 10.0, 0.0, 3, True)
+            assert (lab_d[b] == want).all() and (lab_h[b] == want).all(), b
+    finally:
+        clear_engine_cache()
+
+
 def test_lab_full_colour_cube(port):
     """All 2^24 colours as one 4096x4096 image, against the oracle (which is pinned to the reference)."""
     v = np.arange(1 << 24, dtype=np.uint32)
