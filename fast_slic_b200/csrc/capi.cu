@@ -66,12 +66,14 @@ struct fslic_ctx {
     fslic_cluster* d_cl = nullptr;
     uint16_t* d_lab = nullptr;
     cudaStream_t own_stream = nullptr, in_stream = nullptr, out_stream = nullptr, side_stream = nullptr;
-    cudaEvent_t side_fork = nullptr, side_join = nullptr;
+    cudaEvent_t side_fork = nullptr, side_join = nullptr, tail_done = nullptr;
+    CcaCounters* h_counters = nullptr;  // pinned, 64 entries: lets the host path learn which images need the replay
     std::vector<cudaEvent_t> pipe_ev;  // [2 * chunks]: input-ready / compute-done events of iterate_host
     // timing
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     float stage_ms[FSLIC_T_COUNT] = {0, 0, 0, 0, 0, 0};
     int last_launches = 0;
+    int slice = 0;  // first image of the batch slice the front half (Lab + passes) currently works on
     int max_smem_optin = 0;
     // per-launch timing of the dominant kernel (k_assign_tiles on the subsampled passes)
     std::vector<cudaEvent_t> kev;
@@ -133,6 +135,8 @@ extern "C" int fslic_b200_destroy(fslic_ctx* c) {
     if (c->side_stream) cudaStreamDestroy(c->side_stream);
     if (c->side_fork) cudaEventDestroy(c->side_fork);
     if (c->side_join) cudaEventDestroy(c->side_join);
+    if (c->tail_done) cudaEventDestroy(c->tail_done);
+    if (c->h_counters) cudaFreeHost(c->h_counters);
     for (auto& e : c->pipe_ev) cudaEventDestroy(e);
     delete c;
     return FSLIC_OK;
@@ -219,6 +223,8 @@ extern "C" int fslic_b200_create(int device, int H, int W, int K, int max_batch,
     CKC(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
     CKC(cudaEventCreateWithFlags(&c->side_fork, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&c->side_join, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&c->tail_done, cudaEventDisableTiming));
+    CKC(cudaMallocHost(reinterpret_cast<void**>(&c->h_counters), 64 * sizeof(CcaCounters)));
 
     // opt in to large dynamic shared memory once
     for (int ts : {128, 192, 256, 384})
@@ -271,8 +277,16 @@ extern "C" int fslic_b200_rgb_to_quad(fslic_ctx* c, const uint8_t* d_images, uin
 }
 
 // ---- connectivity enforcement over `batch` images, chunked by cca_batch -------------------------
+// Host-output hook of run_cca (iterate_host only): label maps are copied to the host as soon as they are final --
+// for the images k_cca_threshold settled that is while the std::partial_sort replay of the others still runs.
+struct HostOut {
+    uint16_t* h_labels;      // destination of image 0 of this call
+    cudaStream_t out_stream;
+    bool done;               // set when run_cca issued the label copies itself
+};
+
 static int run_cca(fslic_ctx* c, const uint16_t* d_in, uint16_t* d_out, int batch, int K, int thres, cudaStream_t st,
-                   int* launches) {
+                   int* launches, HostOut* ho = nullptr) {
     const int N = c->N;
     CcaParams cp;
     cp.H = c->H; cp.W = c->W; cp.N = N; cp.K = K; cp.thres = thres; cp.which = -1;
@@ -325,14 +339,44 @@ static int run_cca(fslic_ctx* c, const uint16_t* d_in, uint16_t* d_out, int batc
             k_cca_output<<<go, 256, 0, ts>>>(cq, c->par, c->fin, out, c->counters);
         };
         const bool split = nb >= 4;
+        const bool early = split && ho && batch <= c->cca_batch && nb <= 64;
+        if (early) {
+            // the host path is synchronous anyway: wait for the threshold decision and read the per-image flags
+            CK(cudaMemcpyAsync(c->h_counters, c->counters, sizeof(CcaCounters) * nb, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+        }
         if (split) {
             CK(cudaEventRecord(c->side_fork, st));
             CK(cudaStreamWaitEvent(c->side_stream, c->side_fork, 0));
             tail(0, c->side_stream);
             CK(cudaEventRecord(c->side_join, c->side_stream));
         }
+        auto copy_runs = [&](int want) -> int {  // D2H of maximal runs of images whose need_sim flag == want
+            int b = 0;
+            while (b < nb) {
+                if ((c->h_counters[b].need_sim != 0) != (want != 0)) { b++; continue; }
+                int e = b;
+                while (e < nb && (c->h_counters[e].need_sim != 0) == (want != 0)) e++;
+                CK(cudaMemcpyAsync(ho->h_labels + (size_t)b * N, out + (size_t)b * N, (size_t)(e - b) * N * 2,
+                                   cudaMemcpyDeviceToHost, ho->out_stream));
+                b = e;
+            }
+            return FSLIC_OK;
+        };
+        if (early) {
+            CK(cudaStreamWaitEvent(ho->out_stream, c->side_join, 0));
+            int rc2 = copy_runs(0);
+            if (rc2) return rc2;
+        }
         k_cca_select<<<nb, 1024, SEL_CHUNK * 8 + (cp.heap_in_smem ? heap_bytes : 0), st>>>(cp, c->carea, c->counters, c->heap);
         tail(split ? 1 : -1, st);
+        if (early) {
+            CK(cudaEventRecord(c->tail_done, st));
+            CK(cudaStreamWaitEvent(ho->out_stream, c->tail_done, 0));
+            int rc2 = copy_runs(1);
+            if (rc2) return rc2;
+            ho->done = true;
+        }
         if (split) {
             CK(cudaStreamWaitEvent(st, c->side_join, 0));
             if (launches) *launches += 5;
@@ -365,6 +409,13 @@ extern "C" int fslic_b200_debug_heap_select(fslic_ctx* c, const int32_t* d_area,
     CK(cudaGetLastError());
     return FSLIC_OK;
 }
+
+// per-slice views of the batched buffers (c->slice = first image of the slice)
+#define SL_QUAD(c) ((c)->quad + (size_t)(c)->slice * (c)->N)
+#define SL_LABELS(c) ((c)->labels + (size_t)(c)->slice * (c)->N)
+#define SL_CINFO(c) ((c)->cinfo + (size_t)(c)->slice * (c)->K)
+#define SL_CELLS(c) ((c)->cell_start + (size_t)(c)->slice * ((c)->ncell + 1))
+#define SL_ACC(c) ((c)->acc + (size_t)(c)->slice * (c)->K * 4)
 
 // ---- one assign pass (warp kernel, or the generic kernel when the patch cannot live in shared memory) ----
 struct PassGeom {
@@ -462,18 +513,18 @@ static int run_assign_pass(fslic_ctx* c, int batch, int stride, int rem, int cfg
             e1 = c->kev[c->kev_used++];
             CK(cudaEventRecord(e0, st));
         }
-        fn<<<(int)grid, AS_THREADS, g.smem, st>>>(ap, c->quad, c->labels, c->cinfo, c->cell_start, c->acc, tbl);
+        fn<<<(int)grid, AS_THREADS, g.smem, st>>>(ap, SL_QUAD(c), SL_LABELS(c), SL_CINFO(c), SL_CELLS(c), SL_ACC(c), tbl);
         if (e1) CK(cudaEventRecord(e1, st));
     } else {
         const long px = (long)ap.nsub * c->W * batch;
         long grid = (px + 255) / 256;
         if (grid > (long)c->num_sms * 64) grid = (long)c->num_sms * 64;
         if (update)
-            k_assign_generic<true><<<(int)grid, 256, 0, st>>>(ap, c->quad, c->labels, c->cinfo, c->cell_start,
-                                                              c->acc);
+            k_assign_generic<true><<<(int)grid, 256, 0, st>>>(ap, SL_QUAD(c), SL_LABELS(c), SL_CINFO(c), SL_CELLS(c),
+                                                              SL_ACC(c));
         else
-            k_assign_generic<false><<<(int)grid, 256, 0, st>>>(ap, c->quad, c->labels, c->cinfo, c->cell_start,
-                                                               c->acc);
+            k_assign_generic<false><<<(int)grid, 256, 0, st>>>(ap, SL_QUAD(c), SL_LABELS(c), SL_CINFO(c), SL_CELLS(c),
+                                                               SL_ACC(c));
     }
     if (launches) *launches += 1;
     CK(cudaGetLastError());
@@ -487,22 +538,18 @@ static int run_prepare(fslic_ctx* c, fslic_cluster* d_clusters, int batch, int f
     pp.G = c->G; pp.cellW = c->cellW; pp.cellH = c->cellH; pp.ncell = c->ncell;
     pp.first = first; pp.finalize = finalize; pp.last = 0;
     const size_t smem = (size_t)(c->ncell + 2) * sizeof(int);
-    k_prepare<<<batch, 1024, smem, st>>>(pp, d_clusters, c->acc, c->quad, c->cinfo, c->cell_start, c->cinfo_tmp);
+    k_prepare<<<batch, 1024, smem, st>>>(pp, d_clusters, SL_ACC(c), SL_QUAD(c), SL_CINFO(c), SL_CELLS(c),
+                                         c->cinfo_tmp + (size_t)c->slice * c->K);
     CK(cudaGetLastError());
     if (launches) *launches += 1;
     return FSLIC_OK;
 }
 
-extern "C" int fslic_b200_iterate(fslic_ctx* c, const uint8_t* d_images, fslic_cluster* d_clusters, uint16_t* d_labels,
-                                  int batch, const fslic_params* p, void* stream) {
-    int rc = check_batch(c, batch);
-    if (rc) return rc;
+static int check_params(const fslic_ctx* c, const fslic_params* p, float* coef_out) {
     if (!p) return set_err(FSLIC_EINVAL, "params is NULL");
     if (p->subsample_stride <= 0 || p->subsample_stride > 255) return set_err(FSLIC_EINVAL, "subsample_stride must be in 1..255");
     if (p->max_iter < 0) return set_err(FSLIC_EINVAL, "max_iter must be >= 0");
     if (!(p->compactness >= 0.f)) return set_err(FSLIC_EINVAL, "compactness must be >= 0");
-    CK(cudaSetDevice(c->device));
-    cudaStream_t st = (cudaStream_t)stream;
     const int S = c->S;
     const int color_shift = p->convert_to_lab ? 1 : 0;  // cielab.h:25,352 / context.cpp:127
     // BaseContext::set_spatial_patch, context.cpp:25-26 (same float operations, same order)
@@ -511,34 +558,63 @@ extern "C" int fslic_b200_iterate(fslic_ctx* c, const uint8_t* d_images, fslic_c
     if (S > 0 && !(coef * (float)(2 * S) < (float)(FSLIC_BIGSP - 766)))
         return set_err(FSLIC_ERANGE, "compactness too large: the u16 distance of the reference would overflow");
     if (S == 0) coef = 0.f;  // 1/(0/compactness) = inf in the reference; with S == 0 only m = 0 is ever used -> inf*0 = NaN -> (u16) UB; use 0
+    *coef_out = coef;
+    return FSLIC_OK;
+}
+
+// Front half of iterate (context.cpp:114-181): Lab LUT, max_iter x (assign + update), full assign, for the
+// `batch` images starting at image `b0` of the context's buffers.  Leaves the pre-CCA labels in c->labels.
+static int iterate_front(fslic_ctx* c, int b0, const uint8_t* d_images, fslic_cluster* d_clusters, int batch,
+                         const fslic_params* p, float coef, cudaStream_t st, int* launches, bool timing) {
+    c->slice = b0;
+    int rc = launch_lab(c, d_images, SL_QUAD(c), batch, p->convert_to_lab, st);
+    if (rc) return rc;
+    (*launches)++;
+    if (timing) CK(cudaEventRecord(c->ev[1], st));
+    const int stride = p->subsample_stride;
+    rc = build_patches(c, stride, p->max_iter > 0, coef, st, launches);
+    if (rc) return rc;
+    int rem = 0;
+    for (int it = 0; it < p->max_iter; it++) {
+        rc = run_prepare(c, d_clusters, batch, it == 0, it > 0, st, launches);
+        if (rc) return rc;
+        rc = run_assign_pass(c, batch, stride, rem, stride, it, true, coef, st, launches);
+        if (rc) return rc;
+        rem = (rem + 1) % stride;
+    }
+    if (timing) CK(cudaEventRecord(c->ev[2], st));
+    rc = run_prepare(c, d_clusters, batch, p->max_iter == 0, p->max_iter > 0, st, launches);
+    if (rc) return rc;
+    rc = run_assign_pass(c, batch, 1, 0, stride, p->max_iter < stride ? p->max_iter : stride, false, coef, st, launches);
+    c->slice = 0;
+    return rc;
+}
+
+// Back half (context.cpp:191-194): connectivity enforcement of images [0, batch) of c->labels into d_labels.
+static int iterate_back(fslic_ctx* c, uint16_t* d_labels, int batch, const fslic_params* p, cudaStream_t st, int* launches,
+                        HostOut* ho = nullptr) {
+    const int thres = (int)round((double)(c->S * c->S) * (double)p->min_size_factor);  // context.cpp:16
+    return run_cca(c, c->labels, d_labels, batch, c->K, thres, st, launches, ho);
+}
+
+extern "C" int fslic_b200_iterate(fslic_ctx* c, const uint8_t* d_images, fslic_cluster* d_clusters, uint16_t* d_labels,
+                                  int batch, const fslic_params* p, void* stream) {
+    int rc = check_batch(c, batch);
+    if (rc) return rc;
+    float coef;
+    rc = check_params(c, p, &coef);
+    if (rc) return rc;
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
     int launches = 0;
     const bool timing = p->collect_timing != 0;
     c->kev_on = p->collect_timing >= 2;
     c->kev_used = 0;
     if (timing) CK(cudaEventRecord(c->ev[0], st));
-    rc = launch_lab(c, d_images, c->quad, batch, p->convert_to_lab, st);
-    if (rc) return rc;
-    launches++;
-    if (timing) CK(cudaEventRecord(c->ev[1], st));
-    const int stride = p->subsample_stride;
-    rc = build_patches(c, stride, p->max_iter > 0, coef, st, &launches);
-    if (rc) return rc;
-    int rem = 0;
-    for (int it = 0; it < p->max_iter; it++) {
-        rc = run_prepare(c, d_clusters, batch, it == 0, it > 0, st, &launches);
-        if (rc) return rc;
-        rc = run_assign_pass(c, batch, stride, rem, stride, it, true, coef, st, &launches);
-        if (rc) return rc;
-        rem = (rem + 1) % stride;
-    }
-    if (timing) CK(cudaEventRecord(c->ev[2], st));
-    rc = run_prepare(c, d_clusters, batch, p->max_iter == 0, p->max_iter > 0, st, &launches);
-    if (rc) return rc;
-    rc = run_assign_pass(c, batch, 1, 0, stride, p->max_iter < stride ? p->max_iter : stride, false, coef, st, &launches);
+    rc = iterate_front(c, 0, d_images, d_clusters, batch, p, coef, st, &launches, timing);
     if (rc) return rc;
     if (timing) CK(cudaEventRecord(c->ev[3], st));
-    const int thres = (int)round((double)(S * S) * (double)p->min_size_factor);  // context.cpp:16
-    rc = run_cca(c, c->labels, d_labels, batch, c->K, thres, st, &launches);
+    rc = iterate_back(c, d_labels, batch, p, st, &launches);
     if (rc) return rc;
     if (timing) {
         CK(cudaEventRecord(c->ev[4], st));
@@ -640,7 +716,7 @@ extern "C" int fslic_b200_iterate_host(fslic_ctx* c, const uint8_t* h_images, fs
         if (v >= 1 && v < chunk) chunk = v;
     }
     const int nchunks = (batch + chunk - 1) / chunk;
-    while ((int)c->pipe_ev.size() < 2 * nchunks) {
+    while ((int)c->pipe_ev.size() < 3 * nchunks) {
         cudaEvent_t e;
         CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         c->pipe_ev.push_back(e);
@@ -656,22 +732,60 @@ extern "C" int fslic_b200_iterate_host(fslic_ctx* c, const uint8_t* h_images, fs
     }
     for (int k = 0; k < nchunks; k++) {
         const int b0 = k * chunk, nb = (batch - b0 < chunk) ? (batch - b0) : chunk;
+        // Upload in two halves: the front half of the pipeline (Lab + passes) of the first half runs while the
+        // second half is still on the wire; the back half (connectivity enforcement, whose replay latency is per
+        // launch, not per image) then runs once over the whole chunk.
+        bool labels_copied = false;
+        static const bool no_split = getenv("FSLIC_HOST_SPLIT") && atoi(getenv("FSLIC_HOST_SPLIT")) == 0;
+        if (nb >= 8 && !no_split) {
+            float coef;
+            rc = check_params(c, &pp, &coef);
+            if (rc) return rc;
+            int launches = 0;
+            const int h0 = nb / 2;
+            for (int hpart = 0; hpart < 2; hpart++) {
+                const int s0 = b0 + (hpart ? h0 : 0), sn = hpart ? nb - h0 : h0;
+                CK(cudaMemcpyAsync(c->d_img + (size_t)s0 * N * 3, h_images + (size_t)s0 * N * 3, (size_t)sn * N * 3,
+                                   cudaMemcpyHostToDevice, c->in_stream));
+                CK(cudaMemcpyAsync(c->d_cl + (size_t)s0 * c->K, h_clusters + (size_t)s0 * c->K,
+                                   (size_t)sn * c->K * sizeof(fslic_cluster), cudaMemcpyHostToDevice, c->in_stream));
+                cudaEvent_t ev = hpart ? c->pipe_ev[3 * k] : c->pipe_ev[3 * k + 2];
+                CK(cudaEventRecord(ev, c->in_stream));
+                if (trace && hpart == 1) cudaEventRecord(tev[1 + 4 * k], c->in_stream);
+                CK(cudaStreamWaitEvent(c->own_stream, ev, 0));
+                if (trace && hpart == 0) cudaEventRecord(tev[2 + 4 * k], c->own_stream);
+                // slice s0 - b0 of the context buffers <-> images s0 .. s0+sn of this chunk
+                rc = iterate_front(c, s0 - b0, c->d_img + (size_t)s0 * N * 3, c->d_cl + (size_t)s0 * c->K, sn, &pp, coef,
+                                   c->own_stream, &launches, false);
+                if (rc) return rc;
+            }
+            HostOut ho;
+            ho.h_labels = h_labels + (size_t)b0 * N;
+            ho.out_stream = c->out_stream;
+            ho.done = false;
+            rc = iterate_back(c, c->d_lab + (size_t)b0 * N, nb, &pp, c->own_stream, &launches, &ho);
+            if (rc) return rc;
+            labels_copied = ho.done;
+            c->last_launches = launches;
+        } else {
         CK(cudaMemcpyAsync(c->d_img + (size_t)b0 * N * 3, h_images + (size_t)b0 * N * 3, (size_t)nb * N * 3,
                            cudaMemcpyHostToDevice, c->in_stream));
         CK(cudaMemcpyAsync(c->d_cl + (size_t)b0 * c->K, h_clusters + (size_t)b0 * c->K,
                            (size_t)nb * c->K * sizeof(fslic_cluster), cudaMemcpyHostToDevice, c->in_stream));
-        CK(cudaEventRecord(c->pipe_ev[2 * k], c->in_stream));
+        CK(cudaEventRecord(c->pipe_ev[3 * k], c->in_stream));
         if (trace) cudaEventRecord(tev[1 + 4 * k], c->in_stream);
-        CK(cudaStreamWaitEvent(c->own_stream, c->pipe_ev[2 * k], 0));
+        CK(cudaStreamWaitEvent(c->own_stream, c->pipe_ev[3 * k], 0));
         if (trace) cudaEventRecord(tev[2 + 4 * k], c->own_stream);
         rc = fslic_b200_iterate(c, c->d_img + (size_t)b0 * N * 3, c->d_cl + (size_t)b0 * c->K, c->d_lab + (size_t)b0 * N, nb,
                                 &pp, c->own_stream);
         if (rc) return rc;
-        CK(cudaEventRecord(c->pipe_ev[2 * k + 1], c->own_stream));
+        }
+        CK(cudaEventRecord(c->pipe_ev[3 * k + 1], c->own_stream));
         if (trace) cudaEventRecord(tev[3 + 4 * k], c->own_stream);
-        CK(cudaStreamWaitEvent(c->out_stream, c->pipe_ev[2 * k + 1], 0));
-        CK(cudaMemcpyAsync(h_labels + (size_t)b0 * N, c->d_lab + (size_t)b0 * N, (size_t)nb * N * 2, cudaMemcpyDeviceToHost,
-                           c->out_stream));
+        CK(cudaStreamWaitEvent(c->out_stream, c->pipe_ev[3 * k + 1], 0));
+        if (!labels_copied)
+            CK(cudaMemcpyAsync(h_labels + (size_t)b0 * N, c->d_lab + (size_t)b0 * N, (size_t)nb * N * 2, cudaMemcpyDeviceToHost,
+                               c->out_stream));
         CK(cudaMemcpyAsync(h_clusters + (size_t)b0 * c->K, c->d_cl + (size_t)b0 * c->K,
                            (size_t)nb * c->K * sizeof(fslic_cluster), cudaMemcpyDeviceToHost, c->out_stream));
         if (trace) cudaEventRecord(tev[4 + 4 * k], c->out_stream);
