@@ -742,6 +742,8 @@ extern "C" int fslic_b200_iterate_host(fslic_ctx* c, const uint8_t* h_images, fs
             rc = check_params(c, &pp, &coef);
             if (rc) return rc;
             int launches = 0;
+            c->kev_on = false;  // per-launch kernel timing belongs to fslic_b200_iterate(collect_timing >= 2) only
+            c->kev_used = 0;
             const int h0 = nb / 2;
             for (int hpart = 0; hpart < 2; hpart++) {
                 const int s0 = b0 + (hpart ? h0 : 0), sn = hpart ? nb - h0 : h0;
