@@ -369,8 +369,14 @@ def main():
     alg_bytes = 6.0 * sub_px                               # 4 B quad read + 2 B label written per pixel
     avg_ms = k_ms / max(k_n, 1)
     achieved = alg_bytes / (avg_ms * 1e-3) / 1e9 if k_n else 0.0
+    traffic = None  # dram__bytes_read + dram__bytes_write per launch, from the committed ncu --set full capture
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_assign_traffic.json")))
+        traffic = tj.get("%s_batch%d" % (args.workload, B), {}).get("traffic")
+    except Exception:
+        pass
     roofline = {"kernel": "k_assign_warp<TS,3,true> (fused assign+update, subsampled pass)", "bound": "hbm",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "bytes_per_launch": alg_bytes, "avg_launch_us": avg_ms * 1e3,
                 "launches_timed": k_n, "stage_ms_last_step": stage}
 
