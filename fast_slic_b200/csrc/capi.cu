@@ -157,6 +157,10 @@ extern "C" int fslic_b200_create(int device, int H, int W, int K, int max_batch,
     c->device = device;
     c->H = H; c->W = W; c->K = K; c->maxB = max_batch; c->N = H * W;
     c->S = (int)(int16_t)sqrt((double)(H * W / K));  // context.h:60 (integer division first)
+    if (c->S < 1) {  // the reference divides by zero here (PreemptiveGrid: ceil_int(W, 2*S), preemptive.h:37-38)
+        delete c;
+        return set_err(FSLIC_EINVAL, "num_components exceeds the number of pixels (S = 0): the reference crashes on this input");
+    }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
         c->num_sms = prop.multiProcessorCount;

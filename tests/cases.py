@@ -42,6 +42,22 @@ PIPELINE_CASES = [
     ("speckle_240x320_K100_msf0", "syn", 240, 320, 100, dict(min_size_factor=0.0, sigma=40.0)),
 ]
 
+# shapes and parameters off the beaten path (each verified oracle == compiled reference when added)
+EDGE_CASES = [
+    ("tiny_5x7_K3", "noise", 5, 7, 3, {}),
+    ("row_1x200_K7", "syn", 1, 200, 7, {}),
+    ("col_200x1_K7", "syn", 200, 1, 7, {}),
+    ("denseK_96x128_K6000", "noise", 96, 128, 6000, dict(min_size_factor=0.0)),
+    ("S1_20x20_K300", "noise", 20, 20, 300, dict(min_size_factor=0.0)),
+    ("stride255_it3", "syn", 300, 200, 40, dict(subsample_stride=255, max_iter=3)),
+    ("compact0.01", "syn", 120, 160, 30, dict(compactness=0.01)),
+    ("compact2000", "syn", 120, 160, 30, dict(compactness=2000.0)),
+    ("it25", "syn", 100, 140, 25, dict(max_iter=25)),
+    ("msf3_everything_absorbed", "noise", 100, 140, 25, dict(min_size_factor=3.0)),
+    ("w33", "syn", 70, 33, 9, {}),
+    ("w31", "syn", 70, 31, 9, {}),
+]
+
 BIG_CASES = [
     ("B_1280x720_K1600_msf0", "syn", 720, 1280, 1600, dict(min_size_factor=0.0)),
     ("B_1280x720_K1600_msf.1_s40", "syn", 720, 1280, 1600, dict(min_size_factor=0.1, sigma=40.0)),

@@ -10,7 +10,7 @@ import sys
 import numpy as np
 import pytest
 
-from cases import PIPELINE_CASES, make_image, split_kwargs
+from cases import EDGE_CASES, PIPELINE_CASES, make_image, split_kwargs
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden", "golden_v1.npz")
@@ -60,6 +60,17 @@ def test_oracle_matches_compiled_reference(port, ref, case):
     o1, q1, p1 = port.iterate(img, c1, *args, stages=True)
     o2, q2, p2 = ref.iterate(img, c2, *args, stages=True, num_threads=2)
     assert (q1 == q2).all() and (p1 == p2).all() and (o1 == o2).all() and c1.tobytes() == c2.tobytes()
+
+
+@pytest.mark.parametrize("case", EDGE_CASES, ids=[c[0] for c in EDGE_CASES])
+def test_oracle_matches_compiled_reference_edge(port, ref, case):
+    name, kind, H, W, K, kw = case
+    sigma, a = split_kwargs(kw)
+    img = make_image(kind, H, W, seed=5, sigma=sigma)
+    c1, c2 = port.initialize(img, K), ref.initialize(img, K)
+    args = (a["max_iter"], a["compactness"], a["min_size_factor"], a["subsample_stride"], a["convert_to_lab"])
+    o1, o2 = port.iterate(img, c1, *args), ref.iterate(img, c2, *args, num_threads=2)
+    assert (o1 == o2).all() and c1.tobytes() == c2.tobytes()
 
 
 def test_reference_thread_and_arch_invariance(ref):

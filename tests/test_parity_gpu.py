@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from cases import BIG_CASES, PIPELINE_CASES, make_image, split_kwargs
+from cases import BIG_CASES, EDGE_CASES, PIPELINE_CASES, make_image, split_kwargs
 
 pytestmark = pytest.mark.gpu
 
@@ -63,6 +63,24 @@ def test_pipeline_parity(port, case):
     sigma, args = split_kwargs(kw)
     img = make_image(kind, H, W, seed=7, sigma=sigma)
     _compare(name, _run_cuda(img, K, args), _run_oracle(port, img, K, args))
+
+
+@pytest.mark.parametrize("case", EDGE_CASES, ids=[c[0] for c in EDGE_CASES])
+def test_pipeline_parity_edge(port, case):
+    name, kind, H, W, K, kw = case
+    sigma, args = split_kwargs(kw)
+    img = make_image(kind, H, W, seed=5, sigma=sigma)
+    _compare(name, _run_cuda(img, K, args), _run_oracle(port, img, K, args))
+
+
+def test_rejects_what_the_reference_cannot_do():
+    """K > H*W makes S = 0: the reference divides by zero there (preemptive.h:37-38); compactness beyond the u16
+    distance range is undefined behaviour in the reference (context.cpp:30).  Both are refused, not guessed."""
+    from fast_slic_b200 import Slic
+    with pytest.raises(ValueError):
+        Slic(num_components=50).iterate(np.zeros((6, 6, 3), np.uint8))
+    with pytest.raises(Exception):
+        Slic(num_components=30, compactness=1e6).iterate(np.zeros((64, 64, 3), np.uint8))
 
 
 @pytest.mark.parametrize("case", BIG_CASES, ids=[c[0] for c in BIG_CASES])
