@@ -656,7 +656,6 @@ __device__ __forceinline__ void heap_select_body(const uint32_t* __restrict__ ar
                 uint32_t haddr = heap.s + 8u, vlo = 0, vhi = 0;
                 int qpos = consumed, next_lane = 0;
                 const int depth = 32 - __clz(K);
-                int idle = depth;
                 const uint32_t q_saddr = (uint32_t)__cvta_generic_to_shared(s_queue);
                 const uint32_t base = heap.s;
                 auto level_step = [&]() {
@@ -672,39 +671,39 @@ __device__ __forceinline__ void heap_select_body(const uint32_t* __restrict__ ar
                     act = mv;
                     __syncwarp();
                 };
-                while (qpos < qn || idle < depth) {
+                // main loop: one (attempted) issue per iteration.  Fast path: the very next queue element beats the
+                // root (the common case: the filter already removed most that cannot); otherwise every lane looks
+                // at one element of the window [qpos, qpos+32) and whole windows are skipped at once -- elements
+                // that do not beat the root now never will, the root only grows.
+                while (qpos < qn) {
                     level_step();
-                    // every lane looks at one queue element of the window [qpos, qpos+32): elements that do not beat
-                    // the root now never will (the root only grows), so whole windows are skipped at once
-                    uint32_t elo = 0, ehi = 0, root_area = 0xffffffffu;
-                    const bool have = qpos < qn;
-                    if (have) {
-                        if (qpos + lane < qn)
-                            asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(elo), "=r"(ehi) : "r"(q_saddr + 8u * (uint32_t)(qpos + lane)));
-                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(root_area) : "r"(base + 12u));
-                    }
+                    uint32_t elo = 0, ehi = 0, root_area;
+                    if (qpos + lane < qn)
+                        asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(elo), "=r"(ehi) : "r"(q_saddr + 8u * (uint32_t)(qpos + lane)));
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(root_area) : "r"(base + 12u));
                     level_step();
-                    idle += 2;
-                    if (have) {
-                        const unsigned hit = __ballot_sync(FSLIC_FULL, (qpos + lane < qn) && (ehi > root_area));
-                        if (hit == 0) {
-                            qpos += 32;
-                        } else {
-                            const int first = __ffs(hit) - 1;  // comp(i, first): __pop_heap(first, middle, i)
-                            const uint32_t ilo = __shfl_sync(FSLIC_FULL, elo, first);
-                            const uint32_t ihi = __shfl_sync(FSLIC_FULL, ehi, first);
-                            if (lane == next_lane) {
-                                act = true;
-                                haddr = base + 8u;
-                                vlo = ilo;
-                                vhi = ihi;
-                            }
-                            next_lane = (next_lane + 1) & 31;
-                            nops++;
-                            idle = 0;
-                            qpos += first + 1;
+                    const unsigned hit = __ballot_sync(FSLIC_FULL, ehi > root_area);  // lanes past qn hold ehi = 0
+                    if (hit == 0) {
+                        qpos += 32;
+                    } else {
+                        const int first = __ffs(hit) - 1;  // comp(i, first): __pop_heap(first, middle, i)
+                        const uint32_t ilo = __shfl_sync(FSLIC_FULL, elo, first);
+                        const uint32_t ihi = __shfl_sync(FSLIC_FULL, ehi, first);
+                        if (lane == next_lane) {
+                            act = true;
+                            haddr = base + 8u;
+                            vlo = ilo;
+                            vhi = ihi;
                         }
+                        next_lane = (next_lane + 1) & 31;
+                        nops++;
+                        qpos += first + 1;
                     }
+                }
+                // drain: no sift-down takes more than `depth` levels
+                for (int d = 0; d < depth; d += 2) {
+                    level_step();
+                    level_step();
                 }
             } else {
             bool act = false;
