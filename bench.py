@@ -415,11 +415,41 @@ def main():
         e2e_step_tight(i)
         per_step.append(time.perf_counter() - ts)
     torch.cuda.synchronize()
+    dt_block = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    h2d = B * (H * W * 3 + K * 32)
+    d2h = B * (H * W * 2 + K * 32)
+
+    # streaming form of the same call: two contexts, fslic_b200_iterate_host_async / fslic_b200_wait alternating, so
+    # one batch's PCIe copies overlap the other's kernels.  Every step still uploads its own images + clusters and
+    # downloads its own labels + clusters inside the timed region.
+    from fast_slic_b200 import Engine
+    slots = [(eng, work_u8, work_cl, lab_np)]
+    eng_b = Engine(H, W, K, B, local_rank)
+    wu_b = torch.empty(pristine.shape, dtype=torch.uint8).pin_memory().numpy()
+    slots.append((eng_b, wu_b, wu_b.view(CLUSTER_DTYPE).reshape(B, K),
+                  torch.empty((B, H, W), dtype=torch.int16).pin_memory().numpy()))
+
+    def e2e_submit(i):
+        e, wu, wcl, lab = slots[i % 2]
+        e.wait()                                               # results of step i-2 are in host memory
+        wu[...] = cl_u8
+        e.iterate_host_async(host_np[i % n_host], wcl, p_fast, lab)
+
+    for i in range(max(args.warmup, 2)):
+        e2e_submit(i)
+    for e, _, _, _ in slots:
+        e.wait()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_submit(i)
+    for e, _, _, _ in slots:
+        e.wait()
     dt = max_over_ranks(time.perf_counter() - t0)
     barrier()
     e2e_value = world * B * args.steps * MP / dt
-    h2d = B * (H * W * 3 + K * 32)
-    d2h = B * (H * W * 2 + K * 32)
+    eng_b.close()
 
     # ---- informational: batched throughput on the same image shape ----
     batched = None
@@ -490,9 +520,16 @@ def main():
                        "parallelism": "independent images per rank, no data-path collective"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "megapixels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * dt / args.steps, "ms_per_step_median": 1e3 * float(np.median(per_step)),
-                    "ms_per_step_min": 1e3 * float(np.min(per_step)),
-                    "api": "fslic_b200_iterate_host via fast_slic_b200.Engine.iterate_host (pinned host buffers)",
+                    "ms_per_step": 1e3 * dt / args.steps,
+                    "api": "fslic_b200_iterate_host_async + fslic_b200_wait (fast_slic_b200.Engine), two contexts "
+                           "alternating, pinned host buffers; every step uploads its images+clusters and downloads "
+                           "its labels+clusters inside the timed region",
+                    "blocking": {"value": world * B * args.steps * MP / dt_block, "unit": "megapixels/s",
+                                 "ms_per_step": 1e3 * dt_block / args.steps,
+                                 "ms_per_step_median": 1e3 * float(np.median(per_step)),
+                                 "ms_per_step_min": 1e3 * float(np.min(per_step)),
+                                 "api": "fslic_b200_iterate_host (one blocking call per step, like the reference's "
+                                        "iterate())"},
                     "numa": numa},
             "gpu_launches": launches,
             "roofline": roofline,

@@ -16,6 +16,7 @@ EXPORTED_SYMBOLS = (
     "fslic_b200_initialize_clusters_host", "fslic_b200_enforce_connectivity", "fslic_b200_debug_stages",
     "fslic_b200_rgb_to_quad", "fslic_b200_debug_heap_select", "fslic_b200_stage_ms", "fslic_b200_get_S",
     "fslic_b200_launches_last_iterate", "fslic_b200_assign_kernel_time", "fslic_b200_debug_cca_counters",
+    "fslic_b200_iterate_host_async", "fslic_b200_wait",
 )
 
 STAGE_NAMES = ("cielab_conversion", "assign", "update", "full_assign", "enforce_connectivity", "iterate")
@@ -58,6 +59,8 @@ def lib():
     L.fslic_b200_initialize_clusters.argtypes = [vp, vp, vp, i32, vp]
     L.fslic_b200_iterate.argtypes = [vp, vp, vp, vp, i32, C.POINTER(Params), vp]
     L.fslic_b200_iterate_host.argtypes = [vp, vp, vp, vp, i32, C.POINTER(Params)]
+    L.fslic_b200_iterate_host_async.argtypes = [vp, vp, vp, vp, i32, C.POINTER(Params)]
+    L.fslic_b200_wait.argtypes = [vp]
     L.fslic_b200_initialize_clusters_host.argtypes = [vp, vp, vp, i32]
     L.fslic_b200_enforce_connectivity.argtypes = [vp, vp, i32, i32, i32, vp]
     L.fslic_b200_debug_stages.argtypes = [vp, vp, vp, i32, vp]

@@ -79,6 +79,7 @@ struct fslic_ctx {
     std::vector<cudaEvent_t> kev;
     int kev_used = 0;
     bool kev_on = false;
+    bool pending = false;  // an iterate_host_async batch is in flight on this context's streams
     float assign_kernel_ms = 0.f;
     int assign_kernel_launches = 0;
 };
@@ -701,13 +702,21 @@ extern "C" int fslic_b200_initialize_clusters_host(fslic_ctx* c, const uint8_t* 
     return FSLIC_OK;
 }
 
-extern "C" int fslic_b200_iterate_host(fslic_ctx* c, const uint8_t* h_images, fslic_cluster* h_clusters,
-                                       uint16_t* h_labels, int batch, const fslic_params* p) {
+// Enqueues H2D -> kernels -> D2H for one host batch on the context's three streams.  With may_sync the caller is
+// going to block anyway, so the connectivity stage may read its per-image decisions back mid-way and start the
+// label download of settled images early; without it nothing here waits for the device.
+static int iterate_host_enqueue(fslic_ctx* c, const uint8_t* h_images, fslic_cluster* h_clusters, uint16_t* h_labels,
+                                int batch, const fslic_params* p, bool may_sync) {
     int rc = check_batch(c, batch);
     if (rc) return rc;
     CK(cudaSetDevice(c->device));
     rc = ensure_staging(c);
     if (rc) return rc;
+    if (c->pending) {  // one batch in flight per context: its staging buffers are about to be overwritten
+        CK(cudaStreamSynchronize(c->out_stream));
+        CK(cudaStreamSynchronize(c->own_stream));
+        c->pending = false;
+    }
     // Software pipeline over chunks of the batch: H2D(chunk i+1) | compute(chunk i) | D2H(chunk i-1) on three
     // streams, so for batches the PCIe copies hide behind the kernels (and vice versa).  With pinned host
     // buffers the copies are truly asynchronous; pageable buffers still work, just without overlap.
@@ -727,7 +736,7 @@ extern "C" int fslic_b200_iterate_host(fslic_ctx* c, const uint8_t* h_images, fs
     }
     fslic_params pp = *p;
     if (nchunks > 1) pp.collect_timing = 0;  // per-stage timings are only meaningful for an unchunked run
-    const bool trace = getenv("FSLIC_TRACE") != nullptr;
+    const bool trace = may_sync && getenv("FSLIC_TRACE") != nullptr;
     std::vector<cudaEvent_t> tev;
     if (trace) {
         tev.resize(1 + 4 * nchunks);
@@ -769,7 +778,7 @@ extern "C" int fslic_b200_iterate_host(fslic_ctx* c, const uint8_t* h_images, fs
             ho.h_labels = h_labels + (size_t)b0 * N;
             ho.out_stream = c->out_stream;
             ho.done = false;
-            rc = iterate_back(c, c->d_lab + (size_t)b0 * N, nb, &pp, c->own_stream, &launches, &ho);
+            rc = iterate_back(c, c->d_lab + (size_t)b0 * N, nb, &pp, c->own_stream, &launches, may_sync ? &ho : nullptr);
             if (rc) return rc;
             labels_copied = ho.done;
             c->last_launches = launches;
@@ -796,8 +805,11 @@ extern "C" int fslic_b200_iterate_host(fslic_ctx* c, const uint8_t* h_images, fs
                            (size_t)nb * c->K * sizeof(fslic_cluster), cudaMemcpyDeviceToHost, c->out_stream));
         if (trace) cudaEventRecord(tev[4 + 4 * k], c->out_stream);
     }
+    c->pending = true;
+    if (!may_sync) return FSLIC_OK;
     CK(cudaStreamSynchronize(c->out_stream));
     CK(cudaStreamSynchronize(c->own_stream));
+    c->pending = false;
     if (trace) {
         float ms;
         for (int k = 0; k < nchunks; k++) {
@@ -811,5 +823,25 @@ extern "C" int fslic_b200_iterate_host(fslic_ctx* c, const uint8_t* h_images, fs
         (void)ms;
         for (auto e : tev) cudaEventDestroy(e);
     }
+    return FSLIC_OK;
+}
+
+extern "C" int fslic_b200_iterate_host(fslic_ctx* c, const uint8_t* h_images, fslic_cluster* h_clusters,
+                                       uint16_t* h_labels, int batch, const fslic_params* p) {
+    return iterate_host_enqueue(c, h_images, h_clusters, h_labels, batch, p, true);
+}
+
+extern "C" int fslic_b200_iterate_host_async(fslic_ctx* c, const uint8_t* h_images, fslic_cluster* h_clusters,
+                                             uint16_t* h_labels, int batch, const fslic_params* p) {
+    return iterate_host_enqueue(c, h_images, h_clusters, h_labels, batch, p, false);
+}
+
+extern "C" int fslic_b200_wait(fslic_ctx* c) {
+    if (!c) return set_err(FSLIC_EINVAL, "ctx is NULL");
+    if (!c->pending) return FSLIC_OK;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->out_stream));
+    CK(cudaStreamSynchronize(c->own_stream));
+    c->pending = false;
     return FSLIC_OK;
 }

@@ -133,6 +133,17 @@ class Engine:
                                               labels_np.ctypes.data, B, C.byref(params)))
         return labels_np
 
+    def iterate_host_async(self, images_np, clusters_np, params, labels_np):
+        """Enqueue one host batch and return; `wait()` blocks until labels_np / clusters_np are filled.
+        All three arrays must live in pinned memory and must not be touched in between."""
+        self._inflight = (images_np, clusters_np, labels_np, params)  # keep the buffers alive
+        check(self._L.fslic_b200_iterate_host_async(self._h, images_np.ctypes.data, clusters_np.ctypes.data,
+                                                    labels_np.ctypes.data, images_np.shape[0], C.byref(params)))
+
+    def wait(self):
+        check(self._L.fslic_b200_wait(self._h))
+        self._inflight = None
+
     def stage_ms(self):
         out = (C.c_float * 6)()
         check(self._L.fslic_b200_stage_ms(self._h, out, 6))

@@ -92,6 +92,15 @@ int fslic_b200_iterate_host(fslic_ctx* ctx, const uint8_t* h_images, fslic_clust
 int fslic_b200_initialize_clusters_host(fslic_ctx* ctx, const uint8_t* h_images, fslic_cluster* h_clusters,
                                         int batch);
 
+/* Streaming form of fslic_b200_iterate_host (no counterpart in the reference, whose iterate() blocks): enqueue
+ * the same H2D -> kernels -> D2H work and return at once; fslic_b200_wait() blocks until the labels and clusters
+ * are in the host buffers.  The host buffers must be pinned and stay untouched until then.  One batch per
+ * context may be in flight (a second _async call waits for the first); a caller that alternates between two
+ * contexts overlaps one batch's PCIe copies with the other's kernels. */
+int fslic_b200_iterate_host_async(fslic_ctx* ctx, const uint8_t* h_images, fslic_cluster* h_clusters,
+                                  uint16_t* h_labels, int batch, const fslic_params* params);
+int fslic_b200_wait(fslic_ctx* ctx);
+
 /* == cca::ConnectivityEnforcer(labels,H,W,K,min_threshold).execute(labels) (cca.cpp:178-265),
  *    in place on d_labels [B,H,W] u16.  H, W come from the context; K (= max label + 1 in
  *    cfast_slic.pyx:377-382) is given by the caller. */
