@@ -88,6 +88,9 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=32, help="images per step per GPU")
     ap.add_argument("--sigma", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--contexts", type=int, default=3,
+                    help="independent batches in flight per GPU (contexts used round-robin, one stream each); "
+                         "1 = strictly one step after the other")
     ap.add_argument("--extra-batched", type=int, default=1,
                     help="also report throughput at this batch size (0 = skip); default 1 = single-image latency")
     return ap.parse_args()
@@ -328,26 +331,64 @@ def main():
         eng.iterate(pool[i % pool_steps], clusters, params, labels)
 
     # ---- kernel-resident throughput: inputs already in HBM ----
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.wait_first()
+    # (1) one step after the other on one stream
     for i in range(args.warmup):
         step(i, p_fast)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    if sampler:
-        sampler.mark_begin()
     e0.record()
     for i in range(args.steps):
         step(args.warmup + i, p_fast)
     e1.record()
     barrier()
+    ms_seq = max_over_ranks(e0.elapsed_time(e1))
+    launches = eng.launches_last_iterate() * args.steps
+
+    # (2) the same K steps issued round-robin over NCTX contexts, one stream each: successive batches are
+    # independent, so the latency-bound stretch of one (the std::partial_sort replay) runs under the
+    # bandwidth-hungry kernels of the next.  Timed with events on the launching stream: fork before, join after.
+    from fast_slic_b200 import Engine
+    NCTX = max(1, args.contexts)
+    lanes = [(eng, clusters, labels, torch.cuda.Stream(device))]
+    for _ in range(NCTX - 1):
+        lanes.append((Engine(H, W, K, B, local_rank), pristine.clone(), torch.empty_like(labels), torch.cuda.Stream(device)))
+
+    def lane_step(i):
+        e, cl, lab, st = lanes[i % NCTX]
+        with torch.cuda.stream(st):
+            cl.copy_(pristine, non_blocking=True)
+            e.iterate(pool[i % pool_steps], cl, p_fast, lab)
+
+    def fork_join(n, first):
+        main = torch.cuda.current_stream(device)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(main)
+        for _, _, _, st in lanes:
+            st.wait_event(a)
+        for i in range(n):
+            lane_step(first + i)
+        for _, _, _, st in lanes:
+            j = torch.cuda.Event()
+            j.record(st)
+            main.wait_event(j)
+        b.record(main)
+        return a, b
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.wait_first()
+    fork_join(max(args.warmup, NCTX), 0)
+    barrier()
+    barrier()
+    if sampler:
+        sampler.mark_begin()
+    e0, e1 = fork_join(args.steps, args.warmup)
+    barrier()
     if sampler:
         sampler.mark_end()
     ms = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if sampler else None
-    launches = eng.launches_last_iterate() * args.steps
     value = world * B * args.steps * MP / (ms / 1e3)
 
     # ---- roofline of the dominant kernel: per-launch CUDA events on the launch stream, same workload ----
@@ -425,18 +466,18 @@ def main():
     # downloads its own labels + clusters inside the timed region.
     from fast_slic_b200 import Engine
     slots = [(eng, work_u8, work_cl, lab_np)]
-    eng_b = Engine(H, W, K, B, local_rank)
-    wu_b = torch.empty(pristine.shape, dtype=torch.uint8).pin_memory().numpy()
-    slots.append((eng_b, wu_b, wu_b.view(CLUSTER_DTYPE).reshape(B, K),
-                  torch.empty((B, H, W), dtype=torch.int16).pin_memory().numpy()))
+    for lane in lanes[1:]:
+        wu_b = torch.empty(pristine.shape, dtype=torch.uint8).pin_memory().numpy()
+        slots.append((lane[0], wu_b, wu_b.view(CLUSTER_DTYPE).reshape(B, K),
+                      torch.empty((B, H, W), dtype=torch.int16).pin_memory().numpy()))
 
     def e2e_submit(i):
-        e, wu, wcl, lab = slots[i % 2]
+        e, wu, wcl, lab = slots[i % NCTX]
         e.wait()                                               # results of step i-2 are in host memory
         wu[...] = cl_u8
         e.iterate_host_async(host_np[i % n_host], wcl, p_fast, lab)
 
-    for i in range(max(args.warmup, 2)):
+    for i in range(max(args.warmup, NCTX)):
         e2e_submit(i)
     for e, _, _, _ in slots:
         e.wait()
@@ -449,7 +490,6 @@ def main():
     dt = max_over_ranks(time.perf_counter() - t0)
     barrier()
     e2e_value = world * B * args.steps * MP / dt
-    eng_b.close()
 
     # ---- informational: batched throughput on the same image shape ----
     batched = None
@@ -517,13 +557,17 @@ def main():
                                    "batch=%d image(s)/step/GPU (BASELINE configs[1])" % (W, H, K, msf, B),
                        "l2": "inputs rotate through a %d MB pool of distinct images (> 126 MB L2)"
                              % (pool_steps * B * img_bytes // 1000000),
-                       "parallelism": "independent images per rank, no data-path collective"},
+                       "parallelism": "independent images per rank, no data-path collective",
+                       "concurrency": "%d independent batches in flight per GPU (contexts used round-robin, one stream "
+                                      "each); 'sequential' = one step after the other on one stream" % NCTX},
+            "sequential": {"value": world * B * args.steps * MP / (ms_seq / 1e3), "unit": "megapixels/s",
+                           "ms_per_step": ms_seq / args.steps},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "megapixels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * dt / args.steps,
-                    "api": "fslic_b200_iterate_host_async + fslic_b200_wait (fast_slic_b200.Engine), two contexts "
-                           "alternating, pinned host buffers; every step uploads its images+clusters and downloads "
-                           "its labels+clusters inside the timed region",
+                    "api": "fslic_b200_iterate_host_async + fslic_b200_wait (fast_slic_b200.Engine), %d contexts "
+                           "round-robin, pinned host buffers; every step uploads its images+clusters and downloads "
+                           "its labels+clusters inside the timed region" % NCTX,
                     "blocking": {"value": world * B * args.steps * MP / dt_block, "unit": "megapixels/s",
                                  "ms_per_step": 1e3 * dt_block / args.steps,
                                  "ms_per_step_median": 1e3 * float(np.median(per_step)),
