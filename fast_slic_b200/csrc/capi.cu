@@ -54,7 +54,8 @@ struct fslic_ctx {
     int* cleader = nullptr;        // [Bc][N]
     uint32_t* carea = nullptr;     // [Bc][N]
     uint16_t* cnew = nullptr;      // [Bc][N]
-    uint16_t* fin = nullptr;       // [Bc][N]
+    uint16_t* fin = nullptr;       // [Bc][N]  (second half of the cnew allocation)
+    int* rootbuf = nullptr;        // [Bc][N] ordered root lists of k_ccl_flatten; ALIASES cnew + fin (dead until the tail)
     int* blkcnt = nullptr;         // [Bc][nblk]
     int* blkoff = nullptr;         // [Bc][nblk]
     CcaCounters* counters = nullptr;  // [Bc]
@@ -123,7 +124,7 @@ extern "C" int fslic_b200_destroy(fslic_ctx* c) {
     cudaSetDevice(c->device);
     void* ptrs[] = {c->d_gamma, c->d_labtbl, c->quad,   c->labels,  c->cinfo,  c->acc,    c->cell_start,
                     c->cinfo_tmp, c->sptable, c->par,  c->aux,    c->cleader, c->carea,
-                    c->cnew,    c->fin,      c->blkcnt, c->blkoff,  c->counters, c->ahist, c->heap, c->d_img,
+                    c->cnew,    c->blkcnt, c->blkoff,  c->counters, c->ahist, c->heap, c->d_img,
                     c->d_cl,    c->d_lab};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -213,8 +214,9 @@ extern "C" int fslic_b200_create(int device, int H, int W, int K, int max_batch,
     CKC(dalloc(&c->aux, bc * N));
     CKC(dalloc(&c->cleader, bc * N));
     CKC(dalloc(&c->carea, bc * N));
-    CKC(dalloc(&c->cnew, bc * N));
-    CKC(dalloc(&c->fin, bc * N));
+    CKC(dalloc(&c->cnew, 2 * bc * N));
+    c->fin = c->cnew + bc * N;
+    c->rootbuf = reinterpret_cast<int*>(c->cnew);
     CKC(dalloc(&c->blkcnt, bc * nblk));
     CKC(dalloc(&c->blkoff, bc * nblk));
     CKC(dalloc(&c->counters, bc));
@@ -315,10 +317,11 @@ static int run_cca(fslic_ctx* c, const uint16_t* d_in, uint16_t* d_out, int batc
                 k_ccl_seams<<<gs, 256, 0, st>>>(cp, in, c->par);
             }
         }
-        k_ccl_flatten<<<g, 256, 0, st>>>(cp, in, c->par, c->aux, c->blkcnt);
+        k_ccl_flatten<<<g, 256, 0, st>>>(cp, in, c->par, c->aux, c->blkcnt, c->rootbuf);
         k_scan_blocks<<<nb, 1024, 0, st>>>(c->blkcnt, c->blkoff, cp.nblk, cp.nblk, nullptr, 0, 1,
                                            &c->counters[0].ncomp, (int)(sizeof(CcaCounters) / sizeof(int)), nullptr, -1);
-        k_ccl_number<<<g, CCA_BLOCK, 0, st>>>(cp, c->par, c->aux, c->blkoff, c->cleader, c->carea, c->counters, c->ahist);
+        k_ccl_number<<<dim3(CCA_NUMBER_GRID, nb), CCA_BLOCK, 0, st>>>(cp, c->rootbuf, c->aux, c->blkcnt, c->blkoff, c->cleader, c->carea,
+                                                                      c->counters, c->ahist);
         k_cca_threshold<<<nb, 1024, 0, st>>>(cp, c->carea, c->counters, c->ahist);
         // Everything after the threshold decision depends on the kept set.  For images k_cca_threshold settled
         // that is known now; for the (few) images whose ties need the sequential std::partial_sort replay it
@@ -328,17 +331,18 @@ static int run_cca(fslic_ctx* c, const uint16_t* d_in, uint16_t* d_out, int batc
         auto tail = [&](int which, cudaStream_t ts) {
             CcaParams cq = cp;
             cq.which = which;
-            k_kept_count<<<g, CCA_BLOCK, 0, ts>>>(cq, c->carea, c->counters, c->blkcnt);
+            const dim3 gk(cp.nblk < CCA_KEPT_GRID ? cp.nblk : CCA_KEPT_GRID, nb);
+            k_kept_count<<<gk, CCA_BLOCK, 0, ts>>>(cq, c->carea, c->counters, c->blkcnt);
             k_scan_blocks<<<nb, 1024, 0, ts>>>(c->blkcnt, c->blkoff, cp.nblk, 0, &c->counters[0].ncomp,
                                                (int)(sizeof(CcaCounters) / sizeof(int)), CCA_BLOCK,
                                                &c->counters[0].nkept, (int)(sizeof(CcaCounters) / sizeof(int)),
                                                c->counters, which);
-            k_kept_label<<<g, CCA_BLOCK, 0, ts>>>(cq, c->carea, c->counters, c->blkoff, c->cnew);
+            k_kept_label<<<gk, CCA_BLOCK, 0, ts>>>(cq, c->carea, c->counters, c->blkoff, c->cnew);
             int ab = ceil_div(N, 256 * 8);
             if (ab > c->num_sms * 8) ab = c->num_sms * 8;
             dim3 ga(ab, nb);
             k_cca_absorb<<<ga, 256, 0, ts>>>(cq, c->par, c->aux, c->cleader, c->cnew, c->counters, c->fin);
-            int ob = ceil_div(N, 256);
+            int ob = ceil_div(ceil_div(N, 8), 256);  // 8 pixels per thread on the vector path (any N works: grid-stride)
             if (ob > c->num_sms * 32) ob = c->num_sms * 32;
             dim3 go(ob, nb);
             k_cca_output<<<go, 256, 0, ts>>>(cq, c->par, c->fin, out, c->counters);

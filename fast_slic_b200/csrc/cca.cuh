@@ -109,35 +109,38 @@ __device__ __forceinline__ void ccl_union_s(int* par, int a, int b) {
 
 __global__ void __launch_bounds__(256) k_ccl_tile(CcaParams cp, const uint16_t* __restrict__ labels,
                                                    int* __restrict__ par_all, uint32_t* __restrict__ area_all) {
-    // 256 threads per 32 x 32 tile: warp w owns rows w, w+8, w+16, w+24 (more CTAs in flight per SM than one
-    // 1024-thread CTA per tile, which made this kernel latency bound)
+    // 256 threads per 32 x 32 tile (more CTAs in flight per SM than one 1024-thread CTA per tile, which made this
+    // kernel latency bound).  Warp w owns the STRIP of rows 4w .. 4w+3 and links them top-down, compressing each
+    // row right after its unions: vertical hooking otherwise leaves parent chains as deep as a component is tall,
+    // and walking those chains one lane at a time was most of this kernel's instruction count.
     __shared__ uint32_t s_lab[CCL_T][CCL_T + 1];
     __shared__ int s_par[CCL_T * CCL_T];
     const int b = blockIdx.z;
     const int tx = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int j = blockIdx.x * CCL_T + tx;
     uint32_t v[4], left[4];
+    int sl[4];  // lane of the start of this pixel's run (its initial parent)
 #pragma unroll
     for (int r = 0; r < 4; r++) {
-        const int ty = w + 8 * r, i = blockIdx.y * CCL_T + ty;
+        const int ty = 4 * w + r, i = blockIdx.y * CCL_T + ty;
         const bool ok = (i < cp.H) && (j < cp.W);
         // invalid pixels get labels that differ from everything (and from each other along a row / column)
         v[r] = ok ? (uint32_t)labels[(size_t)b * cp.N + (size_t)i * cp.W + j] : (0x10000u + (uint32_t)(ty * CCL_T + tx));
     }
 #pragma unroll
     for (int r = 0; r < 4; r++) {
-        const int ty = w + 8 * r;
+        const int ty = 4 * w + r;
         s_lab[ty][tx] = v[r];
         left[r] = __shfl_up_sync(FSLIC_FULL, v[r], 1);
         const bool start = (tx == 0) || (v[r] != left[r]);
         const unsigned m = __ballot_sync(FSLIC_FULL, start);
-        const int sl = 31 - __clz(m & (0xffffffffu >> (31 - tx)));
-        s_par[ty * CCL_T + tx] = ty * CCL_T + sl;
+        sl[r] = 31 - __clz(m & (0xffffffffu >> (31 - tx)));
+        s_par[ty * CCL_T + tx] = ty * CCL_T + sl[r];
     }
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < 4; r++) {
-        const int ty = w + 8 * r, me = ty * CCL_T + tx;
+        const int ty = 4 * w + r, me = ty * CCL_T + tx;
         if (ty > 0) {
             const uint32_t up = s_lab[ty - 1][tx];
             if (up == v[r]) {
@@ -147,14 +150,34 @@ __global__ void __launch_bounds__(256) k_ccl_tile(CcaParams cp, const uint16_t* 
                 if (need) ccl_union_s(s_par, me - CCL_T, me);
             }
         }
+        __syncwarp();
+        // compress this row's run starts.  Other warps may be hooking entries concurrently: a plain store of an
+        // ancestor over a NON-root entry is harmless (whoever lowered it keeps uniting the old parent's set), but
+        // a root must never be rewritten (that could undo a concurrent hook), hence the rt != me test.
+        if (sl[r] == tx) {
+            const int rt = ccl_find_s(s_par, me);
+            if (rt != me) s_par[me] = rt;
+        }
+        __syncwarp();
     }
     __syncthreads();
+    // only the run starts chase to the root (a pixel's parent is its run start); the rest get it by shuffle
+    int root[4];
 #pragma unroll
     for (int r = 0; r < 4; r++) {
-        const int ty = w + 8 * r, i = blockIdx.y * CCL_T + ty;
+        root[r] = 0;
+        if (sl[r] == tx) {
+            const int me = (4 * w + r) * CCL_T + tx;
+            root[r] = ccl_find_s(s_par, me);
+            s_par[me] = root[r];  // no unions any more: later rows find the strips above already flat
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int ty = 4 * w + r, i = blockIdx.y * CCL_T + ty;
+        const int rt = __shfl_sync(FSLIC_FULL, root[r], sl[r]);
         if (i < cp.H && j < cp.W) {
-            const int root = ccl_find_s(s_par, ty * CCL_T + tx);
-            const int ri = blockIdx.y * CCL_T + (root >> 5), rj = blockIdx.x * CCL_T + (root & 31);
+            const int ri = blockIdx.y * CCL_T + (rt >> 5), rj = blockIdx.x * CCL_T + (rt & 31);
             const size_t p = (size_t)b * cp.N + (size_t)i * cp.W + j;
             par_all[p] = ri * cp.W + rj;
             area_all[p] = 0;
@@ -194,34 +217,36 @@ __global__ void __launch_bounds__(256) k_ccl_seams(CcaParams cp, const uint16_t*
 }
 
 // Block = 1024 consecutive pixels handled by 256 threads: warp w owns the four 32-pixel chunks 4w .. 4w+3
-// (four independent root chases in flight per lane).
+// (four independent root chases in flight per lane).  Besides flattening, the block emits its roots (= component
+// leaders, cca.cpp:118-134) in raster order into rootbuf[blk * 1024 ...] and their count into blkcnt[blk], so that
+// numbering the components afterwards touches the roots only, not every pixel again.
 __global__ void __launch_bounds__(256) k_ccl_flatten(CcaParams cp, const uint16_t* __restrict__ labels,
                                                      int* __restrict__ par_all, uint32_t* __restrict__ area_all,
-                                                     int* __restrict__ blkcnt) {
-    __shared__ int s_cnt;
+                                                     int* __restrict__ blkcnt, int* __restrict__ rootbuf_all) {
+    __shared__ int s_chunk[32];  // roots per 32-pixel chunk
     const int b = blockIdx.y;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_cnt = 0;
-    __syncthreads();
     const uint16_t* lab = labels + (size_t)b * cp.N;
     int* par = par_all + (size_t)b * cp.N;
     int p[4], sl[4], root[4];
-    unsigned m[4];
+    unsigned m[4], rmask[4];
     bool ok[4], start[4];
+    int jcol = (blockIdx.x * CCA_BLOCK + w * 128 + lane) % cp.W;  // column of chunk 0; the others by stepping
 #pragma unroll
     for (int r = 0; r < 4; r++) {
         p[r] = blockIdx.x * CCA_BLOCK + (w * 4 + r) * 32 + lane;
         ok[r] = p[r] < cp.N;
         const uint32_t v = ok[r] ? lab[p[r]] : 0x10000u;
         const uint32_t left = __shfl_up_sync(FSLIC_FULL, v, 1);
-        const int j = ok[r] ? (p[r] % cp.W) : 0;
+        const int j = jcol;
+        jcol += 32;
+        if (jcol >= cp.W) jcol = (cp.W >= 32) ? (jcol - cp.W) : (jcol % cp.W);
         start[r] = (lane == 0) || (j == 0) || (v != left);
         m[r] = __ballot_sync(FSLIC_FULL, start[r]);
         sl[r] = 31 - __clz(m[r] & (0xffffffffu >> (31 - lane)));
     }
 #pragma unroll
     for (int r = 0; r < 4; r++) root[r] = (ok[r] && start[r]) ? ccl_find(par, p[r]) : 0;
-    int nroots = 0;
 #pragma unroll
     for (int r = 0; r < 4; r++) {
         const int rt = __shfl_sync(FSLIC_FULL, root[r], sl[r]);
@@ -237,11 +262,25 @@ __global__ void __launch_bounds__(256) k_ccl_flatten(CcaParams cp, const uint16_
                 isroot = (rt == p[r]);
             }
         }
-        nroots += __popc(__ballot_sync(FSLIC_FULL, isroot));
+        rmask[r] = __ballot_sync(FSLIC_FULL, isroot);
+        if (lane == 0) s_chunk[w * 4 + r] = __popc(rmask[r]);
     }
-    if (lane == 0 && nroots) atomicAdd(&s_cnt, nroots);
     __syncthreads();
-    if (threadIdx.x == 0) blkcnt[(size_t)b * cp.nblk + blockIdx.x] = s_cnt;
+    // every warp scans the 32 chunk counts for itself (no second barrier)
+    const int mine = s_chunk[lane];
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(FSLIC_FULL, incl, o);
+        if (lane >= o) incl += y;
+    }
+    int* rootbuf = rootbuf_all + (size_t)b * cp.N + (size_t)blockIdx.x * CCA_BLOCK;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int base = __shfl_sync(FSLIC_FULL, incl - mine, w * 4 + r);
+        if ((rmask[r] >> lane) & 1u) rootbuf[base + __popc(rmask[r] & ((1u << lane) - 1u))] = p[r];
+    }
+    if (threadIdx.x == 31) blkcnt[(size_t)b * cp.nblk + blockIdx.x] = incl;
 }
 
 // exclusive scan of cnt[0..n) (n = *n_dev if n_dev else n_static), total -> *total_out
@@ -293,57 +332,100 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(const int* __restrict__ cn
     if (tid == 0) total_base[(size_t)b * total_stride_ints] = s_carry;
 }
 
-__global__ void __launch_bounds__(CCA_BLOCK) k_ccl_number(CcaParams cp, const int* __restrict__ par_all,
+// Component numbers (= rank of the leader in raster order): one WARP per 1024-pixel block walks that block's
+// ordered root list.  Also gathers the area and leader arrays by component number and the histogram of candidate
+// areas for k_cca_threshold.
+#define CCA_NUMBER_GRID 16
+__global__ void __launch_bounds__(CCA_BLOCK) k_ccl_number(CcaParams cp, const int* __restrict__ rootbuf_all,
                                                           uint32_t* __restrict__ aux_all,
+                                                          const int* __restrict__ blkcnt,
                                                           const int* __restrict__ blkoff,
                                                           int* __restrict__ cleader_all,
                                                           uint32_t* __restrict__ carea_all,
                                                           CcaCounters* __restrict__ counters,
                                                           unsigned int* __restrict__ ahist_all) {
-    __shared__ int s_warp[32];
     __shared__ int s_cand;
-    __shared__ unsigned int s_hot[32];  // candidate areas 0..31 (the bulk: specks), flushed once per block
-    if (threadIdx.x < 32) s_hot[threadIdx.x] = 0;
+    // candidate areas 0..31 (the bulk: specks) are counted per warp and flushed once per block.  The lanes of a
+    // warp are grouped by value first (MATCH.ANY): thirty lanes doing a shared-memory atomic on the SAME word are
+    // serialised by the LSU at ~20 cycles each, which used to be this kernel's whole run time.
+    __shared__ unsigned int s_hot[CCA_BLOCK / 32][32];
     const int b = blockIdx.y;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int p = blockIdx.x * CCA_BLOCK + tid;
-    const int* par = par_all + (size_t)b * cp.N;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    s_hot[warp][lane] = 0;
+    if (threadIdx.x == 0) s_cand = 0;
+    __syncthreads();
     uint32_t* aux = aux_all + (size_t)b * cp.N;
-    if (tid == 0) s_cand = 0;
-    const bool isroot = (p < cp.N) && (par[p] == p);
-    const unsigned rm = __ballot_sync(FSLIC_FULL, isroot);
-    if (lane == 0) s_warp[warp] = __popc(rm);
-    __syncthreads();
-    if (warp == 0) {
-        int w = s_warp[lane];
-        int x = w;
+    int ncand = 0;
+    // a warp owns NB consecutive 1024-pixel blocks and walks their root lists as ONE flat sequence, NU x 32 roots
+    // per step with all loads of a step in flight together (the kernel is a chain of dependent memory round trips)
+    constexpr int NU = 8;
+    const int wpi = gridDim.x * (CCA_BLOCK / 32);        // warps per image
+    const int NB = (cp.nblk + wpi - 1) / wpi;            // blocks per warp (<= 32 for the images this grid is sized for)
+    for (int blk0 = (blockIdx.x * (CCA_BLOCK / 32) + warp) * NB; blk0 < cp.nblk; blk0 += wpi * NB) {
+        for (int sub = 0; sub < NB; sub += 32) {
+            const int myblk = blk0 + sub + lane;
+            const bool have = (sub + lane < NB) && (myblk < cp.nblk);
+            const int mycnt = have ? blkcnt[(size_t)b * cp.nblk + myblk] : 0;
+            const int myoff = have ? blkoff[(size_t)b * cp.nblk + myblk] : 0;
+            int incl = mycnt;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int y = __shfl_up_sync(FSLIC_FULL, x, o);
-            if (lane >= o) x += y;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(FSLIC_FULL, incl, o);
+                if (lane >= o) incl += y;
+            }
+            const int total = __shfl_sync(FSLIC_FULL, incl, 31);
+            const int nb_here = min(32, NB - sub);
+            for (int r0 = 0; r0 < total; r0 += 32 * NU) {
+                int pp[NU], cc[NU];
+                uint32_t aa[NU];
+#pragma unroll
+                for (int u = 0; u < NU; u++) {
+                    const int r = r0 + 32 * u + lane;
+                    // block of flat index r: the first one whose inclusive prefix exceeds r
+                    int bi = 0;
+                    for (int q = 0; q < nb_here - 1; q++) bi += (r >= __shfl_sync(FSLIC_FULL, incl, q));
+                    const int bincl = __shfl_sync(FSLIC_FULL, incl, bi), bcnt = __shfl_sync(FSLIC_FULL, mycnt, bi);
+                    const int boff = __shfl_sync(FSLIC_FULL, myoff, bi);
+                    const int t = r - (bincl - bcnt);
+                    pp[u] = -1;
+                    if (r < total) {
+                        pp[u] = rootbuf_all[(size_t)b * cp.N + (size_t)(blk0 + sub + bi) * CCA_BLOCK + t];
+                        cc[u] = boff + t;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < NU; u++) aa[u] = pp[u] >= 0 ? aux[pp[u]] : 0u;
+#pragma unroll
+                for (int u = 0; u < NU; u++) {
+                    uint32_t bin = 0xffffffffu;  // not a candidate
+                    if (pp[u] >= 0) {
+                        aux[pp[u]] = (uint32_t)cc[u];  // the area slot of a root now holds its component number
+                        cleader_all[(size_t)b * cp.N + cc[u]] = pp[u];
+                        carea_all[(size_t)b * cp.N + cc[u]] = aa[u];
+                        // histogram of candidate areas: bins 0..2047 exact, bin 2048 = "2048 or more" (k_cca_threshold)
+                        if ((int)aa[u] >= cp.thres) bin = aa[u] < 2048u ? aa[u] : 2048u;
+                    }
+                    const unsigned peers = __match_any_sync(FSLIC_FULL, bin);
+                    if (bin != 0xffffffffu && lane == __ffs(peers) - 1) {
+                        const unsigned n = __popc(peers);
+                        ncand += (int)n;
+                        if (bin < 32u) s_hot[warp][bin] += n;  // group leaders hold distinct bins: no atomic needed
+                        else atomicAdd(&ahist_all[(size_t)b * CCA_HIST + bin], n);
+                    }
+                    __syncwarp();
+                }
+            }
         }
-        s_warp[lane] = x - w;
     }
+    ncand = __reduce_add_sync(FSLIC_FULL, ncand);
+    if (lane == 0 && ncand) atomicAdd(&s_cand, ncand);
     __syncthreads();
-    bool cand = false;
-    if (isroot) {
-        const int c = blkoff[(size_t)b * cp.nblk + blockIdx.x] + s_warp[warp] + __popc(rm & ((1u << lane) - 1));
-        const uint32_t a = aux[p];
-        aux[p] = (uint32_t)c;  // the area slot of a root now holds its component number
-        cleader_all[(size_t)b * cp.N + c] = p;
-        carea_all[(size_t)b * cp.N + c] = a;
-        cand = (int)a >= cp.thres;
-        if (cand) {
-            // histogram of candidate areas: bins 0..2047 exact, bin 2048 = "2048 or more" (k_cca_threshold)
-            if (a < 32u) atomicAdd(&s_hot[a], 1u);
-            else atomicAdd(&ahist_all[(size_t)b * CCA_HIST + (a < 2048u ? a : 2048u)], 1u);
-        }
+    if (threadIdx.x == 0 && s_cand) atomicAdd(&counters[b].ncand, s_cand);
+    if (threadIdx.x < 32) {
+        unsigned int tot = 0;
+        for (int w = 0; w < CCA_BLOCK / 32; w++) tot += s_hot[w][threadIdx.x];
+        if (tot) atomicAdd(&ahist_all[(size_t)b * CCA_HIST + threadIdx.x], tot);
     }
-    const unsigned cm = __ballot_sync(FSLIC_FULL, cand);
-    if (lane == 0 && cm) atomicAdd(&s_cand, __popc(cm));
-    __syncthreads();
-    if (tid == 0 && s_cand) atomicAdd(&counters[b].ncand, s_cand);
-    if (tid < 32 && s_hot[tid]) atomicAdd(&ahist_all[(size_t)b * CCA_HIST + tid], s_hot[tid]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -820,6 +902,9 @@ __device__ __forceinline__ bool cca_is_kept(uint32_t a, int sel_mode, int keep_t
     return sel_mode ? (a >> 31) : ((int)a >= keep_thres);
 }
 
+// (both kernels walk the ncomp components of an image in chunks of 1024 with a small grid: ncomp is a few
+//  thousand for real images, and it is only known on the device)
+#define CCA_KEPT_GRID 16
 __global__ void __launch_bounds__(CCA_BLOCK) k_kept_count(CcaParams cp, const uint32_t* __restrict__ carea_all,
                                                           const CcaCounters* __restrict__ counters,
                                                           int* __restrict__ blkcnt) {
@@ -827,15 +912,17 @@ __global__ void __launch_bounds__(CCA_BLOCK) k_kept_count(CcaParams cp, const ui
     const int b = blockIdx.y;
     if (cca_skip_image(cp, &counters[b])) return;
     const int ncomp = counters[b].ncomp;
-    if (blockIdx.x * CCA_BLOCK >= ncomp) return;
-    if (threadIdx.x == 0) s_cnt = 0;
-    __syncthreads();
-    const int c = blockIdx.x * CCA_BLOCK + threadIdx.x;
-    const bool kept = (c < ncomp) && cca_is_kept(carea_all[(size_t)b * cp.N + c], counters[b].sel_mode, counters[b].keep_thres);
-    const unsigned m = __ballot_sync(FSLIC_FULL, kept);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&s_cnt, __popc(m));
-    __syncthreads();
-    if (threadIdx.x == 0) blkcnt[(size_t)b * cp.nblk + blockIdx.x] = s_cnt;
+    const int sel_mode = counters[b].sel_mode, keep_thres = counters[b].keep_thres;
+    for (int blk = blockIdx.x; blk * CCA_BLOCK < ncomp; blk += gridDim.x) {
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        const int c = blk * CCA_BLOCK + threadIdx.x;
+        const bool kept = (c < ncomp) && cca_is_kept(carea_all[(size_t)b * cp.N + c], sel_mode, keep_thres);
+        const unsigned m = __ballot_sync(FSLIC_FULL, kept);
+        if ((threadIdx.x & 31) == 0 && m) atomicAdd(&s_cnt, __popc(m));
+        __syncthreads();
+        if (threadIdx.x == 0) blkcnt[(size_t)b * cp.nblk + blk] = s_cnt;
+    }
 }
 
 // newlabel[c] = rank among kept (cca.cpp:234-236), 0xFFFF for components that must be absorbed
@@ -847,28 +934,31 @@ __global__ void __launch_bounds__(CCA_BLOCK) k_kept_label(CcaParams cp, const ui
     const int b = blockIdx.y;
     if (cca_skip_image(cp, &counters[b])) return;
     const int ncomp = counters[b].ncomp;
-    if (blockIdx.x * CCA_BLOCK >= ncomp) return;
+    const int sel_mode = counters[b].sel_mode, keep_thres = counters[b].keep_thres;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int c = blockIdx.x * CCA_BLOCK + tid;
-    const bool kept = (c < ncomp) && cca_is_kept(carea_all[(size_t)b * cp.N + c], counters[b].sel_mode, counters[b].keep_thres);
-    const unsigned m = __ballot_sync(FSLIC_FULL, kept);
-    if (lane == 0) s_warp[warp] = __popc(m);
-    __syncthreads();
-    if (warp == 0) {
-        int w = s_warp[lane];
-        int x = w;
+    for (int blk = blockIdx.x; blk * CCA_BLOCK < ncomp; blk += gridDim.x) {
+        const int c = blk * CCA_BLOCK + tid;
+        const bool kept = (c < ncomp) && cca_is_kept(carea_all[(size_t)b * cp.N + c], sel_mode, keep_thres);
+        const unsigned m = __ballot_sync(FSLIC_FULL, kept);
+        __syncthreads();  // s_warp of the previous chunk has been read
+        if (lane == 0) s_warp[warp] = __popc(m);
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_warp[lane];
+            int x = w;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int y = __shfl_up_sync(FSLIC_FULL, x, o);
-            if (lane >= o) x += y;
+            for (int o = 1; o < 32; o <<= 1) {
+                int y = __shfl_up_sync(FSLIC_FULL, x, o);
+                if (lane >= o) x += y;
+            }
+            s_warp[lane] = x - w;
         }
-        s_warp[lane] = x - w;
-    }
-    __syncthreads();
-    if (c < ncomp) {
-        uint16_t v = 0xFFFF;
-        if (kept) v = (uint16_t)(blkoff[(size_t)b * cp.nblk + blockIdx.x] + s_warp[warp] + __popc(m & ((1u << lane) - 1)));
-        cnew_all[(size_t)b * cp.N + c] = v;
+        __syncthreads();
+        if (c < ncomp) {
+            uint16_t v = 0xFFFF;
+            if (kept) v = (uint16_t)(blkoff[(size_t)b * cp.nblk + blk] + s_warp[warp] + __popc(m & ((1u << lane) - 1)));
+            cnew_all[(size_t)b * cp.N + c] = v;
+        }
     }
 }
 
@@ -912,5 +1002,24 @@ __global__ void __launch_bounds__(256) k_cca_output(CcaParams cp, const int* __r
     const int* par = par_all + (size_t)b * cp.N;
     const uint16_t* fin = final_all + (size_t)b * cp.N;
     uint16_t* out = out_all + (size_t)b * cp.N;
+    if ((cp.N & 7) == 0 && (reinterpret_cast<uintptr_t>(out_all) & 15) == 0 && (reinterpret_cast<uintptr_t>(par_all) & 15) == 0) {
+        // 8 pixels per thread: two 16-byte root loads, eight gathers in flight, one 16-byte store
+        for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < cp.N / 8; t += gridDim.x * blockDim.x) {
+            const int4 r0 = reinterpret_cast<const int4*>(par)[2 * t], r1 = reinterpret_cast<const int4*>(par)[2 * t + 1];
+            // neighbours mostly share their root: gather only where the root changes (predicated loads; the
+            // kernel is bound by the one-sector-per-clock rate of scattered L1 accesses, not by bytes)
+            const uint32_t a0 = fin[r0.x];
+            uint32_t a1 = a0, a2, a3, a4, a5, a6, a7;
+            if (r0.y != r0.x) a1 = fin[r0.y];
+            a2 = a1; if (r0.z != r0.y) a2 = fin[r0.z];
+            a3 = a2; if (r0.w != r0.z) a3 = fin[r0.w];
+            a4 = a3; if (r1.x != r0.w) a4 = fin[r1.x];
+            a5 = a4; if (r1.y != r1.x) a5 = fin[r1.y];
+            a6 = a5; if (r1.z != r1.y) a6 = fin[r1.z];
+            a7 = a6; if (r1.w != r1.z) a7 = fin[r1.w];
+            reinterpret_cast<uint4*>(out)[t] = make_uint4(a0 | (a1 << 16), a2 | (a3 << 16), a4 | (a5 << 16), a6 | (a7 << 16));
+        }
+        return;
+    }
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < cp.N; p += gridDim.x * blockDim.x) out[p] = fin[par[p]];
 }
