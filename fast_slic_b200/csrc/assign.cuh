@@ -523,31 +523,15 @@ __global__ void __launch_bounds__(AS_THREADS, 2) k_assign_warp(AssignParams ap, 
 
             // ---- 4. update sums on the tensor cores ----
             if (UPDATE) {
-                // only the candidates that actually won a pixel of this tile take part (typically 3-5 of ~9):
-                // compact their ranks so one 8-wide N tile almost always suffices
-                uint32_t mymask = 0;
-#pragma unroll
-                for (int rr = 0; rr < R; rr++) {
-                    const uint32_t rb = (rw[rr >> 2] >> (8 * (rr & 3))) & 0xff;
-                    mymask |= (rb < 32) ? (1u << rb) : 0u;
-                }
-                const uint32_t used = __reduce_or_sync(FSLIC_FULL, mymask);
-                const int nw = __popc(used);
-                uint32_t cw[AS_RG];  // compact winner index per pixel (0xFF = none)
-#pragma unroll
-                for (int gq = 0; gq < AS_RG; gq++) cw[gq] = 0;
-#pragma unroll
-                for (int rr = 0; rr < R; rr++) {
-                    const uint32_t rb = (rw[rr >> 2] >> (8 * (rr & 3))) & 0xff;
-                    const uint32_t ci = (rb < 32) ? (uint32_t)__popc(used & ((1u << rb) - 1u)) : 0xffu;
-                    cw[rr >> 2] |= ci << (8 * (rr & 3));
-                }
-                // cluster index by compact winner index (scratch: the ranked-away cyx array of this warp)
-                if ((used >> lane) & 1u) s_ucyx[0][__popc(used & ((1u << lane) - 1u))] = (int32_t)s_k[tq][lane];
-                for (int nt = 0; nt * 8 < nw; nt++) {
-                    // D[feature][winner] += A[feature][pixel] * B[pixel][winner];  rows 8..15 of A are zero
+                // D[candidate][feature] += OneHot[candidate][pixel] * F[pixel][feature]   (m16n8k32, u8 x u8 -> s32)
+                //   A = one-hot of the winning rank, built in registers (16 candidates per pass: one pass unless
+                //       the list is longer than 16);  B = [1, row, lane, L, a, b, 0, 0] per pixel, staged in smem.
+                // Lane (g, tig) ends up with features (2 tig, 2 tig + 1) of candidates g and g + 8: exactly the two
+                // halves of packed accumulator word tig -- no compaction of the winners, no shuffles of D.
+                const int n16 = (n + 15) >> 4;
+                for (int nt = 0; nt < n16; nt++) {
                     int d[4] = {0, 0, 0, 0};
-                    const uint32_t mg = (uint32_t)(nt * 8 + g) * 0x01010101u;
+                    const uint32_t mg0 = (uint32_t)(nt * 16 + g) * 0x01010101u, mg1 = mg0 + 0x08080808u;
 #pragma unroll
                     for (int gq = 0; gq < AS_RG; gq++) {
                         // stage this row group's features: [count 1, row index, lane index, L, a, b, 0, 0] per pixel lane
@@ -563,30 +547,28 @@ __global__ void __launch_bounds__(AS_THREADS, 2) k_assign_warp(AssignParams ap, 
                         __syncwarp();
 #pragma unroll
                         for (int s4 = 0; s4 < 4; s4++) {
-                            const uint32_t w0 = __shfl_sync(FSLIC_FULL, cw[gq], 8 * s4 + tig);
-                            const uint32_t w1 = __shfl_sync(FSLIC_FULL, cw[gq], 8 * s4 + 4 + tig);
-                            mma_u8_16x8x32(d, s_feat[8 * s4 + tig][g], 0u, s_feat[8 * s4 + 4 + tig][g], 0u, eq80(w0, mg),
-                                           eq80(w1, mg));
+                            const uint32_t w0 = __shfl_sync(FSLIC_FULL, rw[gq], 8 * s4 + tig);
+                            const uint32_t w1 = __shfl_sync(FSLIC_FULL, rw[gq], 8 * s4 + 4 + tig);
+                            mma_u8_16x8x32(d, eq80(w0, mg0), eq80(w0, mg1), eq80(w1, mg0), eq80(w1, mg1),
+                                           s_feat[8 * s4 + tig][g], s_feat[8 * s4 + 4 + tig][g]);
                         }
                     }
-                    // lane (g, tig): feature g of winners nt*8 + 2*tig (d0) and +1 (d1), scaled by 128.
-                    //   features: 0 n | 1 sum(row idx) | 2 sum(lane idx) | 3 sum L | 4 sum a | 5 sum b
+                    // sums are scaled by 128 (the one-hot byte is 0x80)
 #pragma unroll
                     for (int hh = 0; hh < 2; hh++) {
-                        const int c = nt * 8 + 2 * tig + hh;
-                        const uint32_t v = (uint32_t)d[hh] >> 7;
-                        const uint32_t partner = __shfl_down_sync(FSLIC_FULL, v, 4);  // feature g+1, same winner
-                        const uint32_t cnt = __shfl_sync(FSLIC_FULL, v, tig);        // feature 0, same winner
-                        if (c < nw && g < 6 && (g & 1) == 0) {
+                        const int c = nt * 16 + g + 8 * hh;
+                        const uint32_t v0 = (uint32_t)d[2 * hh] >> 7, v1 = (uint32_t)d[2 * hh + 1] >> 7;
+                        const uint32_t cnt = __shfl_sync(FSLIC_FULL, v0, lane & ~3);  // feature 0 lives in the tig = 0 lane
+                        if (c < n && tig < 3 && cnt != 0) {
                             unsigned long long word;
-                            if (g == 0)
+                            if (tig == 0)
                                 word = (unsigned long long)cnt |
-                                       ((unsigned long long)(cnt * (uint32_t)wi0 + (uint32_t)stride * partner) << 32);
-                            else if (g == 2)
-                                word = (unsigned long long)(cnt * (uint32_t)wj0 + v) | ((unsigned long long)partner << 32);
+                                       ((unsigned long long)(cnt * (uint32_t)wi0 + (uint32_t)stride * v1) << 32);
+                            else if (tig == 1)
+                                word = (unsigned long long)(cnt * (uint32_t)wj0 + v0) | ((unsigned long long)v1 << 32);
                             else
-                                word = (unsigned long long)v | ((unsigned long long)partner << 32);
-                            atomicAdd(&ac[s_ucyx[0][c] * 4 + (g >> 1)], word);
+                                word = (unsigned long long)v0 | ((unsigned long long)v1 << 32);
+                            atomicAdd(&ac[(uint32_t)s_k[tq][c] * 4 + tig], word);
                         }
                     }
                 }
