@@ -88,7 +88,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=32, help="images per step per GPU")
     ap.add_argument("--sigma", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--contexts", type=int, default=3,
+    ap.add_argument("--contexts", type=int, default=4,
                     help="independent batches in flight per GPU (contexts used round-robin, one stream each); "
                          "1 = strictly one step after the other")
     ap.add_argument("--extra-batched", type=int, default=1,

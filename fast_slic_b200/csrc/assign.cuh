@@ -265,21 +265,27 @@ __device__ __forceinline__ void mma_u8_16x8x32(int (&d)[4], uint32_t a0, uint32_
 //      compile-time] -> VABSDIFF4.U8.ACC (colour SAD + spatial) -> IMAD (d << 16 | rank) -> VIMNMX;
 //   3. labels out (STG.U16, 64 B per warp row);
 //   4. update sums (context.cpp:316-327) as an exact int8 tensor-core product
-//        [1, row, lane, L, a, b]^T (features x pixels)  x  one-hot(rank) (pixels x candidates)
-//      (mma.sync m16n8k32 u8 x u8 -> s32, 4 MMAs per 128 pixels and 8 candidates), then 3 RED.64
-//      per cluster that received pixels.  Integer sums are order independent => exact.
+//        one-hot(rank)^T (candidates x pixels)  x  [1, row, lane, L, a, b] (pixels x features)
+//      (mma.sync m16n8k32 u8 x u8 -> s32, 4 MMAs per 128 pixels and 16 candidates); the D fragment of lane
+//      (g, tig) is accumulator word tig of candidates g and g+8, flushed as RED.64 if they received pixels.
+//      Integer sums are order independent => exact.
 // HBM per processed pixel: 4 B quad read + 2 B label written.
 // ---------------------------------------------------------------------------------------------
 #ifndef FSLIC_UPDATE_MATCH
 #define FSLIC_UPDATE_MATCH 0  // 0: int8 tensor-core one-hot product; 1: MATCH.ANY + REDUX per row (measured 1.4x slower, kept for comparison)
 #endif
+#ifndef AS_RG
 #define AS_RG 1  // row groups of 4 sub-rows per lane (R = 4 * AS_RG rows per warp tile)
+#endif
+#ifndef AS_MINB
+#define AS_MINB 2  // resident CTAs per SM the register budget is sized for
+#endif
 #define AS_R (4 * AS_RG)
 #define AS_T 4   // warp tiles per super tile
 #define AS_STAGE_BYTES (AS_WARPS * AS_T * AS_LIST * 22)
 
 template <int TS, int STRIDE, bool UPDATE>
-__global__ void __launch_bounds__(AS_THREADS, 2) k_assign_warp(AssignParams ap, const uint32_t* __restrict__ quad,
+__global__ void __launch_bounds__(AS_THREADS, AS_MINB) k_assign_warp(AssignParams ap, const uint32_t* __restrict__ quad,
                                                                uint16_t* __restrict__ labels,
                                                                const CInfo* __restrict__ cinfo,
                                                                const int* __restrict__ cell_start,
