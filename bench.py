@@ -296,7 +296,20 @@ def main():
     device = torch.device("cuda", local_rank)
     numa = bind_to_gpu_numa_node(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+        # NCCL may print its version banner to stdout when the communicator is created; the contract is ONE JSON
+        # line on stdout, so stdout points at stderr until the first collective is through
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=device)
+            warm = torch.zeros(1, device=device)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     H, W, K, msf = WORKLOADS[args.workload]
     B = max(1, args.batch)
