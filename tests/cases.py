@@ -15,6 +15,11 @@ def make_image(kind, H, W, seed=1, sigma=12.0):
         rng = np.random.RandomState(seed)
         small = rng.randint(0, 4, (H // 8 + 1, W // 8 + 1, 3)) * 60
         return np.ascontiguousarray(np.kron(small, np.ones((8, 8, 1)))[:H, :W].astype(np.uint8))
+    if kind == "tiled":  # large images without float64 H x W x 3 temporaries: a synthetic tile repeated + a coarse ramp
+        base = synthetic_image(540, 960, seed, sigma)
+        img = np.tile(base, ((H + 539) // 540, (W + 959) // 960, 1))[:H, :W]
+        ramp = ((np.arange(H)[:, None] // 7 + np.arange(W)[None, :] // 5) % 23).astype(np.uint16)
+        return np.ascontiguousarray(np.minimum(img + ramp[..., None], 255).astype(np.uint8))
     raise ValueError(kind)
 
 
@@ -62,6 +67,9 @@ BIG_CASES = [
     ("B_1280x720_K1600_msf0", "syn", 720, 1280, 1600, dict(min_size_factor=0.0)),
     ("B_1280x720_K1600_msf.1_s40", "syn", 720, 1280, 1600, dict(min_size_factor=0.1, sigma=40.0)),
     ("C_1920x1080_K2000_msf0", "syn", 1080, 1920, 2000, dict(min_size_factor=0.0)),
+    ("D_3840x2160_K4000_msf0", "tiled", 2160, 3840, 4000, dict(min_size_factor=0.0)),
+    # > 2^24 pixels: more than 32 of the 1024-pixel blocks per numbering warp (k_ccl_number's outer chunk loop)
+    ("huge_4100x4200_K3000_msf.1", "tiled", 4100, 4200, 3000, dict(min_size_factor=0.1, sigma=20.0)),
 ]
 
 
