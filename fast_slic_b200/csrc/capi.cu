@@ -308,8 +308,11 @@ static int run_cca(fslic_ctx* c, const uint16_t* d_in, uint16_t* d_out, int batc
         CK(cudaMemsetAsync(c->counters, 0, sizeof(CcaCounters) * nb, st));
         CK(cudaMemsetAsync(c->ahist, 0, sizeof(unsigned int) * CCA_HIST * nb, st));
         dim3 g(cp.nblk, nb);
-        dim3 gt(ceil_div(c->W, CCL_T), ceil_div(c->H, CCL_T), nb);
-        k_ccl_tile<<<gt, 256, 0, st>>>(cp, in, c->par, c->aux);
+        {
+            const int ttx = ceil_div(c->W, CCL_T), tty = ceil_div(c->H, CCL_T);
+            const long ntt = (long)ttx * tty * nb;
+            k_ccl_tile<<<(int)((ntt + CCL_TW - 1) / CCL_TW), 32 * CCL_TW, 0, st>>>(cp, in, c->par, c->aux, ttx, tty, ntt);
+        }
         {
             const int seam_px = ((c->W - 1) / CCL_T) * c->H + ((c->H - 1) / CCL_T) * c->W;
             if (seam_px > 0) {

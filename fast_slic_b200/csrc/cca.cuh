@@ -107,81 +107,82 @@ __device__ __forceinline__ void ccl_union_s(int* par, int a, int b) {
     }
 }
 
-__global__ void __launch_bounds__(256) k_ccl_tile(CcaParams cp, const uint16_t* __restrict__ labels,
-                                                   int* __restrict__ par_all, uint32_t* __restrict__ area_all) {
-    // 256 threads per 32 x 32 tile (more CTAs in flight per SM than one 1024-thread CTA per tile, which made this
-    // kernel latency bound).  Warp w owns the STRIP of rows 4w .. 4w+3 and links them top-down, compressing each
-    // row right after its unions: vertical hooking otherwise leaves parent chains as deep as a component is tall,
-    // and walking those chains one lane at a time was most of this kernel's instruction count.
-    __shared__ uint32_t s_lab[CCL_T][CCL_T + 1];
-    __shared__ int s_par[CCL_T * CCL_T];
-    const int b = blockIdx.z;
-    const int tx = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int j = blockIdx.x * CCL_T + tx;
-    uint32_t v[4], left[4];
-    int sl[4];  // lane of the start of this pixel's run (its initial parent)
+// One WARP per 32 x 32 tile, rows top-down, lane = column.  A run inherits the smallest root among the runs it
+// touches in the row above (a segmented prefix-min by shuffles); shared-memory union-find is only needed
+// when a run BRIDGES two components that were separate so far.  (The earlier one-thread-per-pixel version spent
+// most of its instructions walking parent chains in divergent union loops, one or two lanes at a time.)
+#define CCL_TW 4  // tiles (= warps) per CTA
+__global__ void __launch_bounds__(32 * CCL_TW) k_ccl_tile(CcaParams cp, const uint16_t* __restrict__ labels,
+                                                          int* __restrict__ par_all, uint32_t* __restrict__ area_all,
+                                                          int tiles_x, int tiles_y, long ntiles_total) {
+    __shared__ int s_par_all[CCL_TW][CCL_T * CCL_T];
+    __shared__ uint16_t s_lab_all[CCL_TW][CCL_T * CCL_T];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long tile = (long)blockIdx.x * CCL_TW + warp;
+    if (tile >= ntiles_total) return;  // no block-wide barrier below
+    int* s_par = s_par_all[warp];
+    uint16_t* s_lab = s_lab_all[warp];
+    const int per_img = tiles_x * tiles_y;
+    const int b = (int)(tile / per_img);
+    const int tl = (int)(tile - (long)b * per_img);
+    const int tyb = tl / tiles_x, txb = tl - tyb * tiles_x;
+    const int j = txb * CCL_T + lane;
+    const bool colok = j < cp.W;
+    const int nrows = min(CCL_T, cp.H - tyb * CCL_T);  // valid rows of this tile (>= 1)
+    const uint16_t* lab = labels + (size_t)b * cp.N + (size_t)(tyb * CCL_T) * cp.W + j;
+    // all rows in flight at once, parked in shared memory (the row loop below stays rolled: unrolled 32 times it
+    // no longer fits the instruction cache)
 #pragma unroll
-    for (int r = 0; r < 4; r++) {
-        const int ty = 4 * w + r, i = blockIdx.y * CCL_T + ty;
-        const bool ok = (i < cp.H) && (j < cp.W);
-        // invalid pixels get labels that differ from everything (and from each other along a row / column)
-        v[r] = ok ? (uint32_t)labels[(size_t)b * cp.N + (size_t)i * cp.W + j] : (0x10000u + (uint32_t)(ty * CCL_T + tx));
+    for (int ty = 0; ty < CCL_T; ty++) {
+        uint16_t x = 0;
+        if (colok && ty < nrows) x = lab[(size_t)ty * cp.W];
+        s_lab[ty * CCL_T + lane] = x;
     }
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-        const int ty = 4 * w + r;
-        s_lab[ty][tx] = v[r];
-        left[r] = __shfl_up_sync(FSLIC_FULL, v[r], 1);
-        const bool start = (tx == 0) || (v[r] != left[r]);
+    __syncwarp();
+    uint32_t up_v = 0xffffffffu, up_left = 0xffffffffu;
+    int up_root = 0;
+#pragma unroll 1
+    for (int ty = 0; ty < CCL_T; ty++) {
+        // invalid pixels get labels that differ from everything
+        const uint32_t cur = (colok && ty < nrows) ? (uint32_t)s_lab[ty * CCL_T + lane] : (0x10000u + (uint32_t)(ty * CCL_T + lane));
+        const uint32_t left = __shfl_up_sync(FSLIC_FULL, cur, 1);
+        const bool start = (lane == 0) || (cur != left);
         const unsigned m = __ballot_sync(FSLIC_FULL, start);
-        sl[r] = 31 - __clz(m & (0xffffffffu >> (31 - tx)));
-        s_par[ty * CCL_T + tx] = ty * CCL_T + sl[r];
-    }
-    __syncthreads();
+        const int sl = 31 - __clz(m & (0xffffffffu >> (31 - lane)));   // first lane of my run
+        const unsigned above = (lane == 31) ? 0u : (m >> (lane + 1));
+        const int end = above ? (lane + __ffs(above) - 1) : 31;        // last lane of my run
+        // a vertical link matters only where a stretch of common columns of the two runs begins
+        const bool conn = (ty > 0) && (up_v == cur);
+        const bool need = conn && ((lane == 0) || (left != cur) || (up_left != up_v));
+        unsigned cand = 0xffffffffu;
+        if (need) cand = (unsigned)ccl_find_s(s_par, up_root);
+        // min over the run: prefix min from the run start, then everyone reads the last lane of the run
+        // (REDUX under per-run lane masks is executed one mask at a time -- WARPSYNC.EXCLUSIVE -- and was slower)
+        unsigned pm = cand;
 #pragma unroll
-    for (int r = 0; r < 4; r++) {
-        const int ty = 4 * w + r, me = ty * CCL_T + tx;
-        if (ty > 0) {
-            const uint32_t up = s_lab[ty - 1][tx];
-            if (up == v[r]) {
-                // (me, up) is implied by the pair one pixel to the left when both runs extend there
-                bool need = (tx == 0) || (left[r] != v[r]);
-                if (!need) need = s_lab[ty - 1][tx - 1] != up;
-                if (need) ccl_union_s(s_par, me - CCL_T, me);
-            }
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned y = __shfl_up_sync(FSLIC_FULL, pm, o);
+            if (lane - o >= sl) pm = min(pm, y);
         }
+        const unsigned rmin = __shfl_sync(FSLIC_FULL, pm, end);
+        const unsigned own = (unsigned)(ty * CCL_T + sl);
+        const int root = (int)(rmin < own ? rmin : own);
+        if (need && cand != (unsigned)root) ccl_union_s(s_par, (int)cand, root);  // bridge
+        s_par[ty * CCL_T + lane] = root;
         __syncwarp();
-        // compress this row's run starts.  Other warps may be hooking entries concurrently: a plain store of an
-        // ancestor over a NON-root entry is harmless (whoever lowered it keeps uniting the old parent's set), but
-        // a root must never be rewritten (that could undo a concurrent hook), hence the rt != me test.
-        if (sl[r] == tx) {
-            const int rt = ccl_find_s(s_par, me);
-            if (rt != me) s_par[me] = rt;
-        }
-        __syncwarp();
+        up_left = left;
+        up_v = cur;
+        up_root = root;
     }
-    __syncthreads();
-    // only the run starts chase to the root (a pixel's parent is its run start); the rest get it by shuffle
-    int root[4];
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-        root[r] = 0;
-        if (sl[r] == tx) {
-            const int me = (4 * w + r) * CCL_T + tx;
-            root[r] = ccl_find_s(s_par, me);
-            s_par[me] = root[r];  // no unions any more: later rows find the strips above already flat
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-        const int ty = 4 * w + r, i = blockIdx.y * CCL_T + ty;
-        const int rt = __shfl_sync(FSLIC_FULL, root[r], sl[r]);
-        if (i < cp.H && j < cp.W) {
-            const int ri = blockIdx.y * CCL_T + (rt >> 5), rj = blockIdx.x * CCL_T + (rt & 31);
-            const size_t p = (size_t)b * cp.N + (size_t)i * cp.W + j;
-            par_all[p] = ri * cp.W + rj;
-            area_all[p] = 0;
-        }
+    if (!colok) return;
+    int* pout = par_all + (size_t)b * cp.N + (size_t)(tyb * CCL_T) * cp.W + j;
+    uint32_t* aout = area_all + (size_t)b * cp.N + (size_t)(tyb * CCL_T) * cp.W + j;
+#pragma unroll 4
+    for (int ty = 0; ty < nrows; ty++) {
+        const int rt = ccl_find_s(s_par, ty * CCL_T + lane);
+        const int ri = tyb * CCL_T + (rt >> 5), rj = txb * CCL_T + (rt & 31);
+        pout[(size_t)ty * cp.W] = ri * cp.W + rj;
+        aout[(size_t)ty * cp.W] = 0;
     }
 }
 
