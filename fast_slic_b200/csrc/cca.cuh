@@ -116,12 +116,10 @@ __global__ void __launch_bounds__(32 * CCL_TW) k_ccl_tile(CcaParams cp, const ui
                                                           int* __restrict__ par_all, uint32_t* __restrict__ area_all,
                                                           int tiles_x, int tiles_y, long ntiles_total) {
     __shared__ int s_par_all[CCL_TW][CCL_T * CCL_T];
-    __shared__ uint16_t s_lab_all[CCL_TW][CCL_T * CCL_T];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long tile = (long)blockIdx.x * CCL_TW + warp;
     if (tile >= ntiles_total) return;  // no block-wide barrier below
     int* s_par = s_par_all[warp];
-    uint16_t* s_lab = s_lab_all[warp];
     const int per_img = tiles_x * tiles_y;
     const int b = (int)(tile / per_img);
     const int tl = (int)(tile - (long)b * per_img);
@@ -130,49 +128,59 @@ __global__ void __launch_bounds__(32 * CCL_TW) k_ccl_tile(CcaParams cp, const ui
     const bool colok = j < cp.W;
     const int nrows = min(CCL_T, cp.H - tyb * CCL_T);  // valid rows of this tile (>= 1)
     const uint16_t* lab = labels + (size_t)b * cp.N + (size_t)(tyb * CCL_T) * cp.W + j;
-    // all rows in flight at once, parked in shared memory (the row loop below stays rolled: unrolled 32 times it
-    // no longer fits the instruction cache)
+    // rows are consumed strictly in order, so the labels are prefetched one group of CCL_G rows ahead in
+    // registers (the row loop is unrolled by CCL_G only: unrolled 32 times it no longer fits the instruction cache)
+    constexpr int CCL_G = 8;
+    uint32_t v[CCL_G], nv[CCL_G];
 #pragma unroll
-    for (int ty = 0; ty < CCL_T; ty++) {
-        uint16_t x = 0;
-        if (colok && ty < nrows) x = lab[(size_t)ty * cp.W];
-        s_lab[ty * CCL_T + lane] = x;
+    for (int k = 0; k < CCL_G; k++) {
+        // invalid pixels get labels that differ from everything
+        v[k] = (colok && k < nrows) ? (uint32_t)lab[(size_t)k * cp.W] : (0x10000u + (uint32_t)(k * CCL_T + lane));
     }
-    __syncwarp();
     uint32_t up_v = 0xffffffffu, up_left = 0xffffffffu;
     int up_root = 0;
 #pragma unroll 1
-    for (int ty = 0; ty < CCL_T; ty++) {
-        // invalid pixels get labels that differ from everything
-        const uint32_t cur = (colok && ty < nrows) ? (uint32_t)s_lab[ty * CCL_T + lane] : (0x10000u + (uint32_t)(ty * CCL_T + lane));
-        const uint32_t left = __shfl_up_sync(FSLIC_FULL, cur, 1);
-        const bool start = (lane == 0) || (cur != left);
-        const unsigned m = __ballot_sync(FSLIC_FULL, start);
-        const int sl = 31 - __clz(m & (0xffffffffu >> (31 - lane)));   // first lane of my run
-        const unsigned above = (lane == 31) ? 0u : (m >> (lane + 1));
-        const int end = above ? (lane + __ffs(above) - 1) : 31;        // last lane of my run
-        // a vertical link matters only where a stretch of common columns of the two runs begins
-        const bool conn = (ty > 0) && (up_v == cur);
-        const bool need = conn && ((lane == 0) || (left != cur) || (up_left != up_v));
-        unsigned cand = 0xffffffffu;
-        if (need) cand = (unsigned)ccl_find_s(s_par, up_root);
-        // min over the run: prefix min from the run start, then everyone reads the last lane of the run
-        // (REDUX under per-run lane masks is executed one mask at a time -- WARPSYNC.EXCLUSIVE -- and was slower)
-        unsigned pm = cand;
+    for (int ty0 = 0; ty0 < CCL_T; ty0 += CCL_G) {
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned y = __shfl_up_sync(FSLIC_FULL, pm, o);
-            if (lane - o >= sl) pm = min(pm, y);
+        for (int k = 0; k < CCL_G; k++) {
+            const int ty = ty0 + CCL_G + k;
+            nv[k] = (colok && ty < nrows) ? (uint32_t)lab[(size_t)ty * cp.W] : (0x10000u + (uint32_t)((ty & (CCL_T - 1)) * CCL_T + lane));
         }
-        const unsigned rmin = __shfl_sync(FSLIC_FULL, pm, end);
-        const unsigned own = (unsigned)(ty * CCL_T + sl);
-        const int root = (int)(rmin < own ? rmin : own);
-        if (need && cand != (unsigned)root) ccl_union_s(s_par, (int)cand, root);  // bridge
-        s_par[ty * CCL_T + lane] = root;
-        __syncwarp();
-        up_left = left;
-        up_v = cur;
-        up_root = root;
+#pragma unroll
+        for (int k = 0; k < CCL_G; k++) {
+            const int ty = ty0 + k;
+            const uint32_t cur = v[k];
+            const uint32_t left = __shfl_up_sync(FSLIC_FULL, cur, 1);
+            const bool start = (lane == 0) || (cur != left);
+            const unsigned m = __ballot_sync(FSLIC_FULL, start);
+            const int sl = 31 - __clz(m & (0xffffffffu >> (31 - lane)));   // first lane of my run
+            const unsigned above = (lane == 31) ? 0u : (m >> (lane + 1));
+            const int end = above ? (lane + __ffs(above) - 1) : 31;        // last lane of my run
+            // a vertical link matters only where a stretch of common columns of the two runs begins
+            const bool conn = (ty > 0) && (up_v == cur);
+            const bool need = conn && ((lane == 0) || (left != cur) || (up_left != up_v));
+            unsigned cand = 0xffffffffu;
+            if (need) cand = (unsigned)ccl_find_s(s_par, up_root);
+            // min over the run: prefix min from the run start, then everyone reads the last lane of the run
+            // (REDUX under per-run lane masks is executed one mask at a time -- WARPSYNC.EXCLUSIVE -- and was slower)
+            unsigned pm = cand;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned y = __shfl_up_sync(FSLIC_FULL, pm, o);
+                if (lane - o >= sl) pm = min(pm, y);
+            }
+            const unsigned rmin = __shfl_sync(FSLIC_FULL, pm, end);
+            const unsigned own = (unsigned)(ty * CCL_T + sl);
+            const int root = (int)(rmin < own ? rmin : own);
+            if (need && cand != (unsigned)root) ccl_union_s(s_par, (int)cand, root);  // bridge
+            s_par[ty * CCL_T + lane] = root;
+            __syncwarp();
+            up_left = left;
+            up_v = cur;
+            up_root = root;
+        }
+#pragma unroll
+        for (int k = 0; k < CCL_G; k++) v[k] = nv[k];
     }
     if (!colok) return;
     int* pout = par_all + (size_t)b * cp.N + (size_t)(tyb * CCL_T) * cp.W + j;
