@@ -17,4 +17,4 @@ timeout 400 python bench.py --impl reference --steps 6 --warmup 3 > $O/${R}_benc
 timeout 400 python bench.py > $O/${R}_bench_n1.json 2> $O/bench_n1.err
 timeout 300 python bench.py --workload D --batch 8 --steps 40 --warmup 5 --no-cpu-baseline --extra-batched 0 > $O/${R}_bench_D8.json 2> $O/bench_D8.err
 timeout 300 python bench.py --workload C --batch 32 --steps 60 --warmup 5 --no-cpu-baseline --extra-batched 0 > $O/${R}_bench_C32.json 2> $O/bench_C32.err
-tail -c 600 $O/${R}_bench_n1.json; echo; tail -2 $O/bench_n1.err $O/bench_ref.err $O/bench_D8.err $O/bench_C32.err
+tail -c 600 $O/${R}_bench_n1.json; echo
