@@ -254,8 +254,28 @@ __global__ void __launch_bounds__(256) k_ccl_flatten(CcaParams cp, const uint16_
         m[r] = __ballot_sync(FSLIC_FULL, start[r]);
         sl[r] = 31 - __clz(m[r] & (0xffffffffu >> (31 - lane)));
     }
+    {   // the four root chases of a lane advance level by level, so up to four parent loads are in flight per lane
+        // (four ccl_find() calls in a row would walk one chain after the other)
+        int q[4];
 #pragma unroll
-    for (int r = 0; r < 4; r++) root[r] = (ok[r] && start[r]) ? ccl_find(par, p[r]) : 0;
+        for (int r = 0; r < 4; r++) {
+            root[r] = p[r];
+            q[r] = (ok[r] && start[r]) ? par[p[r]] : p[r];
+        }
+        for (;;) {
+            bool mv[4], any = false;
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                mv[r] = q[r] != root[r];
+                root[r] = q[r];
+                any |= mv[r];
+            }
+            if (!any) break;
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+                if (mv[r]) q[r] = par[root[r]];
+        }
+    }
 #pragma unroll
     for (int r = 0; r < 4; r++) {
         const int rt = __shfl_sync(FSLIC_FULL, root[r], sl[r]);
