@@ -550,7 +550,38 @@ def main():
                 hcl_u8[...] = hcl0_u8
                 eng.iterate_host(hbr_np[i % n_rot], hcl_np, p_fast, hl_np)
             dtb = max_over_ranks(time.perf_counter() - t0b)
+            # the same host calls, streamed: several independent requests of this size in flight (one context each)
+            n_req = 8
+            req = []
+            for _ in range(n_req):
+                e_r = Engine(H, W, K, EB, local_rank)
+                cl_r = torch.empty(pr.shape, dtype=torch.uint8).pin_memory().numpy()
+                req.append((e_r, cl_r, cl_r.view(CLUSTER_DTYPE).reshape(EB, K),
+                            torch.empty((EB, H, W), dtype=torch.int16).pin_memory().numpy()))
+
+            def req_submit(i):
+                e_r, cu, ccl, lab_r = req[i % n_req]
+                e_r.wait()
+                cu[...] = hcl0_u8
+                e_r.iterate_host_async(hbr_np[i % n_rot], ccl, p_fast, lab_r)
+
+            for i in range(2 * n_req):
+                req_submit(i)
+            for r_ in req:
+                r_[0].wait()
+            nsteps_s = 4 * nsteps_b
+            t0s = time.perf_counter()
+            for i in range(nsteps_s):
+                req_submit(i)
+            for r_ in req:
+                r_[0].wait()
+            dts = max_over_ranks(time.perf_counter() - t0s)
+            for r_ in req:
+                r_[0].close()
             batched = {"batch": EB, "what": "same workload at this batch size (informational)",
+                       "e2e_streamed": {"value": world * EB * nsteps_s * MP / dts, "unit": "megapixels/s",
+                                        "ms_per_step": 1e3 * dts / nsteps_s, "requests_in_flight": n_req,
+                                        "api": "fslic_b200_iterate_host_async / fslic_b200_wait, one context per request"},
                        "value": world * EB * nsteps_b * MP / (bms / 1e3), "unit": "megapixels/s",
                        "ms_per_step": bms / nsteps_b, "e2e_value": world * EB * nsteps_b * MP / dtb,
                        "e2e_ms_per_step": 1e3 * dtb / nsteps_b, "assign_kernel_GBps": ach,
