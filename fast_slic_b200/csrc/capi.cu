@@ -6,6 +6,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <new>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -81,6 +82,15 @@ struct fslic_ctx {
     int kev_used = 0;
     bool kev_on = false;
     bool pending = false;  // an iterate_host_async batch is in flight on this context's streams
+    // small host batches replay one captured CUDA graph per call instead of ~45 launches (FSLIC_GRAPH=0 turns it off)
+    bool graphs_enabled = true;
+    cudaGraphExec_t gexec = nullptr;
+    struct GraphKey {
+        const void *img, *cl, *lab;
+        int batch;
+        fslic_params p;
+    } gkey = {nullptr, nullptr, nullptr, 0, {0.f, 0.f, 0, 0, 0, 0}};
+    int glaunches = 0;
     float assign_kernel_ms = 0.f;
     int assign_kernel_launches = 0;
 };
@@ -138,6 +148,7 @@ extern "C" int fslic_b200_destroy(fslic_ctx* c) {
     if (c->side_fork) cudaEventDestroy(c->side_fork);
     if (c->side_join) cudaEventDestroy(c->side_join);
     if (c->tail_done) cudaEventDestroy(c->tail_done);
+    if (c->gexec) cudaGraphExecDestroy(c->gexec);
     if (c->h_counters) cudaFreeHost(c->h_counters);
     for (auto& e : c->pipe_ev) cudaEventDestroy(e);
     delete c;
@@ -209,6 +220,7 @@ extern "C" int fslic_b200_create(int device, int H, int W, int K, int max_batch,
         if (v >= 1 && (size_t)v < bc) bc = (size_t)v;
     }
     c->cca_batch = (int)bc;
+    if (const char* e = getenv("FSLIC_GRAPH")) c->graphs_enabled = atoi(e) != 0;
     const int nblk = ceil_div(c->N, CCA_BLOCK);
     CKC(dalloc(&c->par, bc * N));
     CKC(dalloc(&c->aux, bc * N));
@@ -709,6 +721,49 @@ extern "C" int fslic_b200_initialize_clusters_host(fslic_ctx* c, const uint8_t* 
     return FSLIC_OK;
 }
 
+// One iterate() of a small batch on the context's own stream, replayed from a captured CUDA graph when the same
+// buffers, batch and parameters come back (the host entry points always use the context's staging buffers, so
+// that is every call after the first).  Falls back to plain launches if the capture fails.
+static int iterate_graphed(fslic_ctx* c, const uint8_t* d_images, fslic_cluster* d_clusters, uint16_t* d_labels, int batch,
+                           const fslic_params* p, cudaStream_t st) {
+    fslic_ctx::GraphKey k;
+    memset(&k, 0, sizeof(k));
+    k.img = d_images; k.cl = d_clusters; k.lab = d_labels; k.batch = batch; k.p = *p;
+    if (c->gexec && memcmp(&k, &c->gkey, sizeof(k)) == 0) {
+        CK(cudaGraphLaunch(c->gexec, st));
+        c->last_launches = c->glaunches;
+        return FSLIC_OK;
+    }
+    if (c->gexec) {
+        cudaGraphExecDestroy(c->gexec);
+        c->gexec = nullptr;
+    }
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        return fslic_b200_iterate(c, d_images, d_clusters, d_labels, batch, p, st);
+    }
+    const int rc = fslic_b200_iterate(c, d_images, d_clusters, d_labels, batch, p, st);
+    cudaGraph_t g = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(st, &g);
+    if (rc != FSLIC_OK || e != cudaSuccess || !g) {
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        if (rc != FSLIC_OK) return rc;  // a parameter error: nothing was launched
+        return fslic_b200_iterate(c, d_images, d_clusters, d_labels, batch, p, st);
+    }
+    const cudaError_t ei = cudaGraphInstantiate(&c->gexec, g, 0);
+    cudaGraphDestroy(g);
+    if (ei != cudaSuccess) {
+        c->gexec = nullptr;
+        cudaGetLastError();
+        return fslic_b200_iterate(c, d_images, d_clusters, d_labels, batch, p, st);
+    }
+    memcpy(&c->gkey, &k, sizeof(k));
+    c->glaunches = c->last_launches;
+    CK(cudaGraphLaunch(c->gexec, st));
+    return FSLIC_OK;
+}
+
 // Enqueues H2D -> kernels -> D2H for one host batch on the context's three streams.  With may_sync the caller is
 // going to block anyway, so the connectivity stage may read its per-image decisions back mid-way and start the
 // label download of settled images early; without it nothing here waits for the device.
@@ -798,8 +853,11 @@ static int iterate_host_enqueue(fslic_ctx* c, const uint8_t* h_images, fslic_clu
         if (trace) cudaEventRecord(tev[1 + 4 * k], c->in_stream);
         CK(cudaStreamWaitEvent(c->own_stream, c->pipe_ev[3 * k], 0));
         if (trace) cudaEventRecord(tev[2 + 4 * k], c->own_stream);
-        rc = fslic_b200_iterate(c, c->d_img + (size_t)b0 * N * 3, c->d_cl + (size_t)b0 * c->K, c->d_lab + (size_t)b0 * N, nb,
-                                &pp, c->own_stream);
+        if (c->graphs_enabled && nb < 4 && nchunks == 1 && pp.collect_timing == 0)  // nb < 4: one stream, no host sync inside
+            rc = iterate_graphed(c, c->d_img, c->d_cl, c->d_lab, nb, &pp, c->own_stream);
+        else
+            rc = fslic_b200_iterate(c, c->d_img + (size_t)b0 * N * 3, c->d_cl + (size_t)b0 * c->K, c->d_lab + (size_t)b0 * N, nb,
+                                    &pp, c->own_stream);
         if (rc) return rc;
         }
         CK(cudaEventRecord(c->pipe_ev[3 * k + 1], c->own_stream));

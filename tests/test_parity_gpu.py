@@ -188,6 +188,38 @@ def test_async_same_context_serialises(port):
     eng.close()
 
 
+def test_graph_replay_small_host_batches(port, monkeypatch):
+    """Host calls with fewer than 4 images replay one captured CUDA graph (default; FSLIC_GRAPH=0 disables).  Same
+    results as the plain launches for changing images (replay), changing parameters (re-capture) and the async entry point."""
+    from fast_slic_b200 import Engine
+    monkeypatch.setenv("FSLIC_GRAPH", "1")
+    H, W, K = 120, 160, 40
+    eng = Engine(H, W, K, 2)
+    for msf in (0.0, 0.3):
+        p = eng.params(10.0, msf, 3, True, 10)
+        for t in range(3):
+            imgs = np.stack([make_image("noise" if (t + b) % 2 else "syn", H, W, seed=300 + 7 * t + b) for b in range(2)])
+            cl = eng.initialize_clusters_host(imgs)
+            lab = eng.iterate_host(imgs, cl, p)
+            for b in range(2):
+                c0 = port.initialize(imgs[b], K)
+                want = port.iterate(imgs[b], c0, 10, 10.0, msf, 3, True)
+                assert (lab[b].view(np.uint16) == want).all(), (msf, t, b)
+                assert cl[b].tobytes() == c0.tobytes()
+    # one image, async entry point, same context: a third graph
+    p = eng.params(10.0, 0.1, 3, True, 10)
+    for t in range(2):
+        img = torch.from_numpy(make_image("syn", H, W, seed=400 + t)[None]).pin_memory()
+        cl = torch.from_numpy(eng.initialize_clusters_host(img.numpy()).view(np.uint8).reshape(1, K, 32)).pin_memory()
+        lab = torch.empty((1, H, W), dtype=torch.int16).pin_memory()
+        eng.iterate_host_async(img.numpy(), cl.numpy(), p, lab.numpy())
+        eng.wait()
+        c0 = port.initialize(img.numpy()[0], K)
+        want = port.iterate(img.numpy()[0], c0, 10, 10.0, 0.1, 3, True)
+        assert (lab.numpy()[0].view(np.uint16) == want).all() and cl.numpy()[0].tobytes() == c0.tobytes()
+    eng.close()
+
+
 def test_lab_full_colour_cube(port):
     """All 2^24 colours as one 4096x4096 image, against the oracle (which is pinned to the reference)."""
     v = np.arange(1 << 24, dtype=np.uint32)
