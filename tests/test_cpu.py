@@ -73,6 +73,23 @@ def test_oracle_matches_compiled_reference_edge(port, ref, case):
     assert (o1 == o2).all() and c1.tobytes() == c2.tobytes()
 
 
+@pytest.mark.parametrize("seed", range(10))
+def test_oracle_matches_compiled_reference_random_configs(port, ref, seed):
+    """Seeded random shapes / K / parameters: the restatement against the compiled reference, all stages."""
+    rng = np.random.RandomState(1000 + seed)
+    H, W = int(rng.randint(20, 160)), int(rng.randint(20, 200))
+    K = int(rng.randint(1, max(2, H * W // 40)))
+    kind = ["syn", "noise", "blocks"][seed % 3]
+    args = (int(rng.randint(0, 13)), float(rng.choice([0.5, 3.0, 10.0, 40.0])), float(rng.choice([0.0, 0.1, 0.25, 1.0])),
+            int(rng.randint(1, 6)), bool(rng.randint(0, 2)))
+    img = make_image(kind, H, W, seed=seed, sigma=float(rng.choice([5.0, 12.0, 30.0])))
+    c1, c2 = port.initialize(img, K), ref.initialize(img, K)
+    assert c1.tobytes() == c2.tobytes()
+    o1, q1, p1 = port.iterate(img, c1, *args, stages=True)
+    o2, q2, p2 = ref.iterate(img, c2, *args, stages=True, num_threads=2)
+    assert (q1 == q2).all() and (p1 == p2).all() and (o1 == o2).all() and c1.tobytes() == c2.tobytes(), (H, W, K, args)
+
+
 def test_reference_thread_and_arch_invariance(ref):
     img = make_image("syn", 120, 160, seed=3)
     outs = []
