@@ -76,6 +76,15 @@ WORKLOADS = {
     "A": (480, 640, 200, 0.25),      # configs[0]
 }
 COMPACTNESS, MAX_ITER, STRIDE = 10.0, 10, 3
+CONFIG_INDEX = {"A": 0, "B": 1, "C": 2, "D": 3, "B_msf0.1": 4}   # BASELINE.json configs[i] each workload's shape comes from
+
+
+def workload_string(name, B):
+    """One string for both arms (the driver compares them): the BASELINE.json config the shape and parameters come
+    from, and how many independent images of it make one step on each GPU."""
+    H, W, K, msf = WORKLOADS[name]
+    return ("%dx%d RGB, K=%d, compactness=10, 10 iters, stride 3, Lab, min_size_factor=%g (BASELINE configs[%d]), "
+            "%d independent image(s)/step/GPU" % (W, H, K, msf, CONFIG_INDEX[name], B))
 
 
 def parse_args():
@@ -93,6 +102,10 @@ def parse_args():
                          "1 = strictly one step after the other")
     ap.add_argument("--extra-batched", type=int, default=1,
                     help="also report throughput at this batch size (0 = skip); default 1 = single-image latency")
+    ap.add_argument("--no-gather", action="store_true",
+                    help="N > 1 only: skip the extra timed loop that all-gathers every step's labels over NCCL")
+    ap.add_argument("--no-parity-check", action="store_true",
+                    help="skip the post-run comparison of one image per arm with the CPU oracle")
     return ap.parse_args()
 
 
@@ -112,6 +125,15 @@ def synth_images_torch(n, H, W, seed, sigma, device):
         img = img + torch.randn((H, W, 3), generator=g, device=device) * sigma
         out[i] = img.clamp(0, 255).to(torch.uint8)
     return out
+
+
+def pool_images_host(n, H, W, seed, sigma):
+    """The first `n` images of the GPU arm's input pool as a host array -- the SAME bytes the GPU arm segments
+    (generated by the same seeded generator on the same kind of device, then copied back).  Without a GPU (this
+    happens only off the bench box) the same formula runs on the CPU generator."""
+    import torch
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))) if torch.cuda.is_available() else torch.device("cpu")
+    return synth_images_torch(n, H, W, seed, sigma, dev).cpu().numpy()
 
 
 class ClockSampler:
@@ -188,6 +210,8 @@ def _ref_impl():
 
 
 def _ref_one(impl, use_ref, img, K, msf, threads):
+    """Seconds of ONE iterate() of the reference on one image.  initialize() -- Context construction + grid seeding,
+    cfast_slic.pyx:124-147 -- is outside the clock, like on the GPU arm."""
     cl = impl.initialize(img, K)
     t0 = time.perf_counter()
     if use_ref:
@@ -197,42 +221,43 @@ def _ref_one(impl, use_ref, img, K, msf, threads):
     return time.perf_counter() - t0
 
 
-def pick_ref_threads(impl, use_ref, img, K, msf):
+def pick_ref_threads(impl, use_ref, imgs, K, msf, reps=5):
     """Thread count that makes the reference fastest on this box (it does not scale past a few cores on small
-    images, and oversubscribing a cgroup quota is catastrophic), from a short sweep up to the usable cores."""
+    images, and oversubscribing a cgroup quota is catastrophic): best of `reps` runs per count, up to the usable cores."""
     if not use_ref:
         return 1, {}
     cores = usable_cores()
     cands = sorted({c for c in (1, 2, 4, 8, 16, 32, 64, cores) if c <= cores})
     best, sweep = (1e9, 1), {}
     for c in cands:
-        _ref_one(impl, use_ref, img, K, msf, c)  # warm the OpenMP pool at this size
-        t = min(_ref_one(impl, use_ref, img, K, msf, c) for _ in range(2))
+        _ref_one(impl, use_ref, imgs[0], K, msf, c)  # warm the OpenMP pool at this size
+        t = min(_ref_one(impl, use_ref, imgs[r % len(imgs)], K, msf, c) for r in range(reps))
         sweep[c] = t
         if t < best[0]:
             best = (t, c)
     return best[1], sweep
 
 
-def cpu_reference_run(H, W, K, msf, sigma, seconds_budget, n_images=4):
+def cpu_reference_run(imgs, K, msf, seconds_budget):
     """Times the reference's CPU implementation (oracle/_ref = unmodified reference compiled from source;
-    falls back to the plain-C port) on this box's host cores.  Bounded sample, one image at a time
-    (the reference has no batch API)."""
-    from oracle.oracle import synthetic_image
+    falls back to the plain-C port) on this box's host cores, on images copied back from the GPU arm's own input
+    pool.  Bounded sample, one image at a time (the reference has no batch API), iterate() only."""
     impl, use_ref = _ref_impl()
-    imgs = [synthetic_image(H, W, 1000 + i, sigma) for i in range(n_images)]
-    threads, sweep = pick_ref_threads(impl, use_ref, imgs[0], K, msf)
+    H, W = imgs[0].shape[:2]
+    threads, sweep = pick_ref_threads(impl, use_ref, imgs, K, msf)
     _ref_one(impl, use_ref, imgs[0], K, msf, threads)
     times, t_start = [], time.perf_counter()
     while len(times) < 3 or (time.perf_counter() - t_start < seconds_budget and len(times) < 400):
-        times.append(_ref_one(impl, use_ref, imgs[len(times) % n_images], K, msf, threads))
+        times.append(_ref_one(impl, use_ref, imgs[len(times) % len(imgs)], K, msf, threads))
     mp = H * W / 1e6
     return {
-        "value": mp / float(np.mean(times)), "best": mp / float(np.min(times)), "unit": "megapixels/s",
-        "cores": threads, "kind": "reference" if use_ref else "port",
-        "sample": "%d x iterate() of one %dx%d K=%d image (mean; SlicAvx2 path, %d OpenMP threads = fastest of the "
-                  "sweep %s on %d usable cores), after warm-up"
-                  % (len(times), W, H, K, threads, {k: round(1e3 * v, 1) for k, v in sweep.items()}, usable_cores()),
+        "value": mp / float(np.mean(times)), "best": mp / float(np.min(times)), "median": mp / float(np.median(times)),
+        "unit": "megapixels/s", "cores": threads, "kind": "reference" if use_ref else "port",
+        "sample": "%d x iterate() (initialize outside the clock) over %d images of the GPU arm's own pool, %dx%d K=%d "
+                  "(mean; SlicAvx2 path, %d OpenMP threads = fastest of the sweep %s [best of 5 each] on %d usable "
+                  "cores), after warm-up"
+                  % (len(times), len(imgs), W, H, K, threads, {k: round(1e3 * v, 1) for k, v in sweep.items()},
+                     usable_cores()),
         "single_thread_value": (mp / sweep[1]) if 1 in sweep else None,
         "ms_per_image": 1e3 * float(np.mean(times)),
     }
@@ -243,34 +268,32 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle.oracle import synthetic_image
     impl, use_ref = _ref_impl()
-    imgs = [synthetic_image(H, W, 1000 + i, args.sigma) for i in range(4)]
-    cores, sweep = pick_ref_threads(impl, use_ref, imgs[0], K, msf)
+    imgs = list(pool_images_host(8, H, W, 1000, args.sigma))     # == rank 0's first 8 pool images on the GPU arm
+    cores, sweep = pick_ref_threads(impl, use_ref, imgs, K, msf)
     per_step = max(1, args.batch)
 
-    def step(i):
-        for b in range(per_step):
-            _ref_one(impl, use_ref, imgs[(i * per_step + b) % len(imgs)], K, msf, cores)
+    def step(i):  # seconds spent inside iterate() for one step's images
+        return sum(_ref_one(impl, use_ref, imgs[(i * per_step + b) % len(imgs)], K, msf, cores) for b in range(per_step))
 
     for i in range(args.warmup):
         step(i)
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        step(i)
-    dt = time.perf_counter() - t0
+    per = [step(i) for i in range(args.steps)]
+    dt = float(np.sum(per))
     value = per_step * args.steps * H * W / 1e6 / dt
     out = {
         "impl": "reference", "metric": "megapixels/sec (10 iters, K=%d)" % K, "value": value, "unit": "megapixels/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "ms_per_step_median": 1e3 * float(np.median(per)),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u16 integer",
         "data": "synthetic",
-        "config": {"workload": "%dx%d RGB, K=%d, compactness=10, 10 iters, stride 3, Lab, min_size_factor=%g, "
-                               "batch=%d image(s)/step (one at a time: the reference has no batch API)" % (W, H, K, msf, per_step)},
+        "config": {"workload": workload_string(args.workload, per_step),
+                   "how": "one image at a time (the reference has no batch API); clock around iterate() only, like the "
+                          "GPU arm; images = the first 8 of the GPU arm's pool (same seeded bytes)"},
         "cpu_baseline": {"value": value, "unit": "megapixels/s", "cores": cores,
                          "kind": "reference" if use_ref else "port",
                          "sample": "%d timed steps of %d image(s), SlicAvx2 path of the unmodified reference, %d OpenMP "
-                                   "threads (fastest of sweep %s; %d usable cores)"
+                                   "threads (fastest of sweep %s, best of 5 each; %d usable cores)"
                                    % (args.steps, per_step, cores, {k: round(1e3 * v, 1) for k, v in sweep.items()},
                                       usable_cores())},
         "e2e": {"value": value, "unit": "megapixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -348,15 +371,18 @@ def main():
     for i in range(args.warmup):
         step(i, p_fast)
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
-    e0.record()
+    marks[0].record()
     for i in range(args.steps):
         step(args.warmup + i, p_fast)
-    e1.record()
+        marks[i + 1].record()
     barrier()
-    ms_seq = max_over_ranks(e0.elapsed_time(e1))
+    ms_seq = max_over_ranks(marks[0].elapsed_time(marks[-1]))
+    seq_steps = [marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps)]
     launches = eng.launches_last_iterate() * args.steps
+    seq_last = (args.warmup + args.steps - 1) % pool_steps     # pool slot of the last sequential step (parity check)
+    seq_out = (labels.clone(), clusters.clone())
 
     # (2) the same K steps issued round-robin over NCTX contexts, one stream each: successive batches are
     # independent, so the latency-bound stretch of one (the std::partial_sort replay) runs under the
@@ -367,8 +393,11 @@ def main():
     for _ in range(NCTX - 1):
         lanes.append((Engine(H, W, K, B, local_rank), pristine.clone(), torch.empty_like(labels), torch.cuda.Stream(device)))
 
+    lane_last = {}
+
     def lane_step(i):
         e, cl, lab, st = lanes[i % NCTX]
+        lane_last[i % NCTX] = i % pool_steps
         with torch.cuda.stream(st):
             cl.copy_(pristine, non_blocking=True)
             e.iterate(pool[i % pool_steps], cl, p_fast, lab)
@@ -403,6 +432,63 @@ def main():
     ms = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if sampler else None
     value = world * B * args.steps * MP / (ms / 1e3)
+    last_lane = (args.warmup + args.steps - 1) % NCTX
+    value_out = (lane_last[last_lane], lanes[last_lane][2].clone(), lanes[last_lane][1].clone())
+
+    # ---- N > 1: the same loop with the one collective the path has -- the final label gather ----
+    # Every step's u16 label maps are all-gathered over NCCL (int16 on the wire) on a side stream, so the gather of
+    # step i overlaps the kernels of step i+1; a lane's label buffer is not reused before its gather has drained.
+    gather = None
+    if world > 1 and not args.no_gather:
+        comm = torch.cuda.Stream(device)
+        gbuf = [torch.empty((world, B, H, W), dtype=torch.int16, device=device) for _ in range(NCTX)]
+        drained = [None] * NCTX
+
+        def gather_step(i):
+            e, cl, lab, st = lanes[i % NCTX]
+            if drained[i % NCTX] is not None:
+                st.wait_event(drained[i % NCTX])            # labels of this lane's previous step have left
+            with torch.cuda.stream(st):
+                cl.copy_(pristine, non_blocking=True)
+                e.iterate(pool[i % pool_steps], cl, p_fast, lab)
+                done = torch.cuda.Event()
+                done.record(st)
+            with torch.cuda.stream(comm):
+                comm.wait_event(done)
+                dist.all_gather_into_tensor(gbuf[i % NCTX].view(-1), lab.view(-1))
+                ev = torch.cuda.Event()
+                ev.record(comm)
+                drained[i % NCTX] = ev
+
+        def gather_run(n, first):
+            main = torch.cuda.current_stream(device)
+            a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(main)
+            for _, _, _, st in lanes:
+                st.wait_event(a)
+            comm.wait_event(a)
+            for i in range(n):
+                gather_step(first + i)
+            for _, _, _, st in lanes:
+                j = torch.cuda.Event(); j.record(st); main.wait_event(j)
+            j = torch.cuda.Event(); j.record(comm); main.wait_event(j)
+            b2.record(main)
+            return a, b2
+
+        gather_run(max(args.warmup, NCTX), 0)
+        barrier()
+        g0, g1 = gather_run(args.steps, args.warmup)
+        barrier()
+        gms = max_over_ranks(g0.elapsed_time(g1))
+        # every rank must now hold every rank's labels of the last step: check one word per rank against the source
+        chk = gbuf[(args.warmup + args.steps - 1) % NCTX]
+        mine = lanes[(args.warmup + args.steps - 1) % NCTX][2]
+        ok = bool((chk[rank] == mine).all().item())
+        gather = {"value": world * B * args.steps * MP / (gms / 1e3), "unit": "megapixels/s",
+                  "ms_per_step": gms / args.steps, "collective": "ncclAllGather of int16 labels [B,H,W] per rank per step "
+                  "(torch.distributed all_gather_into_tensor) on a side stream, overlapped with the next step's kernels",
+                  "bytes_received_per_rank_per_step": (world - 1) * B * H * W * 2, "own_shard_intact": ok,
+                  "without_gather_value": value}
 
     # ---- roofline of the dominant kernel: per-launch CUDA events on the launch stream, same workload ----
     k_ms, k_n = 0.0, 0
@@ -425,7 +511,7 @@ def main():
     achieved = alg_bytes / (avg_ms * 1e-3) / 1e9 if k_n else 0.0
     traffic = None  # dram__bytes_read + dram__bytes_write per launch, from the committed ncu --set full capture
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_assign_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "assign_traffic.json")))
         traffic = tj.get("%s_batch%d" % (args.workload, B), {}).get("traffic")
     except Exception:
         pass
@@ -468,6 +554,8 @@ def main():
         ts = time.perf_counter()
         e2e_step_tight(i)
         per_step.append(time.perf_counter() - ts)
+    blocking_last = (args.steps - 1) % n_host
+    blocking_out = (lab_np[0].copy(), work_u8[0].copy())       # slot 0 is reused by the streamed arm below
     torch.cuda.synchronize()
     dt_block = max_over_ranks(time.perf_counter() - t0)
     barrier()
@@ -501,6 +589,7 @@ def main():
     for e, _, _, _ in slots:
         e.wait()
     dt = max_over_ranks(time.perf_counter() - t0)
+    stream_last = ((args.steps - 1) % n_host, (args.steps - 1) % NCTX)
     barrier()
     e2e_value = world * B * args.steps * MP / dt
 
@@ -589,7 +678,44 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_reference_run(H, W, K, msf, args.sigma, seconds_budget=12.0)
+        cpu = cpu_reference_run(list(pool.view(-1, H, W, 3)[:8].cpu().numpy()), K, msf, seconds_budget=12.0)
+
+    # ---- parity self-check, outside every timed region: image 0 of the LAST timed step of each arm against the CPU
+    # oracle (the compiled reference when oracle/_ref is there).  A fast wrong answer must not print a number.
+    parity = None
+    if not args.no_parity_check:
+        impl, use_ref = _ref_impl()
+
+        def oracle_of(img_u8):
+            cl0 = impl.initialize(img_u8, K)
+            if use_ref:
+                lab0 = impl.iterate(img_u8, cl0, MAX_ITER, COMPACTNESS, msf, STRIDE, True, arch="x64/avx2",
+                                    num_threads=min(8, usable_cores()))
+            else:
+                lab0 = impl.iterate(img_u8, cl0, MAX_ITER, COMPACTNESS, msf, STRIDE, True)
+            return lab0, cl0
+
+        checks = {}
+        cases = {
+            "sequential": (pool[seq_last][0], seq_out[0][0], seq_out[1][0]),
+            "value": (pool[value_out[0]][0], value_out[1][0], value_out[2][0]),
+            "e2e_blocking": (host_imgs[blocking_last][0], torch.from_numpy(blocking_out[0]), torch.from_numpy(blocking_out[1])),
+            "e2e": (host_imgs[stream_last[0]][0], torch.from_numpy(slots[stream_last[1]][3][0]),
+                    torch.from_numpy(slots[stream_last[1]][1][0])),
+        }
+        for name, (img_t, lab_t, cl_t) in cases.items():
+            want_lab, want_cl = oracle_of(np.ascontiguousarray(img_t.cpu().numpy()))
+            got = lab_t.cpu().numpy().view(np.uint16)
+            checks[name] = bool((got == want_lab).all()) and cl_t.cpu().numpy().tobytes() == want_cl.tobytes()
+        parity = {"checked": True, "oracle": "reference" if use_ref else "port", "arms": checks,
+                  "what": "image 0 of the last timed step of each arm: labels and raw Cluster bytes, tolerance 0"}
+        if not all(checks.values()):
+            raise SystemExit("bench.py: PARITY FAILURE on rank %d: %s -- no number is reported" % (rank, checks))
+
+    numa_all = [numa]
+    if world > 1:
+        numa_all = [None] * world
+        dist.all_gather_object(numa_all, numa)
 
     if rank == 0:
         out = {
@@ -597,15 +723,17 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u16 integer",
             "data": "synthetic",
-            "config": {"workload": "%dx%d RGB, K=%d, compactness=10, 10 iters, stride 3, Lab, min_size_factor=%g, "
-                                   "batch=%d image(s)/step/GPU (BASELINE configs[1])" % (W, H, K, msf, B),
+            "config": {"workload": workload_string(args.workload, B),
                        "l2": "inputs rotate through a %d MB pool of distinct images (> 126 MB L2)"
                              % (pool_steps * B * img_bytes // 1000000),
                        "parallelism": "independent images per rank, no data-path collective",
                        "concurrency": "%d independent batches in flight per GPU (contexts used round-robin, one stream "
                                       "each); 'sequential' = one step after the other on one stream" % NCTX},
             "sequential": {"value": world * B * args.steps * MP / (ms_seq / 1e3), "unit": "megapixels/s",
-                           "ms_per_step": ms_seq / args.steps},
+                           "ms_per_step": ms_seq / args.steps, "ms_per_step_median": float(np.median(seq_steps)),
+                           "ms_per_step_min": float(np.min(seq_steps)), "ms_per_step_max": float(np.max(seq_steps))},
+            "parity_checked": bool(parity and parity["checked"]), "parity": parity,
+            "gather": gather,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "megapixels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * dt / args.steps,
@@ -618,7 +746,7 @@ def main():
                                  "ms_per_step_min": 1e3 * float(np.min(per_step)),
                                  "api": "fslic_b200_iterate_host (one blocking call per step, like the reference's "
                                         "iterate())"},
-                    "numa": numa},
+                    "numa": numa_all},
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu,

@@ -16,7 +16,7 @@ EXPORTED_SYMBOLS = (
     "fslic_b200_initialize_clusters_host", "fslic_b200_enforce_connectivity", "fslic_b200_debug_stages",
     "fslic_b200_rgb_to_quad", "fslic_b200_debug_heap_select", "fslic_b200_stage_ms", "fslic_b200_get_S",
     "fslic_b200_launches_last_iterate", "fslic_b200_assign_kernel_time", "fslic_b200_debug_cca_counters",
-    "fslic_b200_iterate_host_async", "fslic_b200_wait",
+    "fslic_b200_iterate_host_async", "fslic_b200_wait", "fslic_b200_create_cca",
 )
 
 STAGE_NAMES = ("cielab_conversion", "assign", "update", "full_assign", "enforce_connectivity", "iterate")
@@ -55,6 +55,7 @@ def lib():
     L.fslic_b200_last_error.restype = C.c_char_p
     L.fslic_b200_version.restype = C.c_char_p
     L.fslic_b200_create.argtypes = [i32, i32, i32, i32, i32, C.POINTER(vp)]
+    L.fslic_b200_create_cca.argtypes = [i32, i32, i32, i32, C.POINTER(vp)]
     L.fslic_b200_destroy.argtypes = [vp]
     L.fslic_b200_initialize_clusters.argtypes = [vp, vp, vp, i32, vp]
     L.fslic_b200_iterate.argtypes = [vp, vp, vp, vp, i32, C.POINTER(Params), vp]

@@ -5,7 +5,10 @@ properties, return dtype) and the Cython ``SlicModel`` (/root/reference/cfast_sl
 attributes cfast_slic.pxd:104-120).  Only the default integer-distance path of the north star is
 implemented; the float-distance / LSC / preemptive variants raise NotImplementedError.
 """
+import collections
+import contextlib
 import json
+import threading
 
 import numpy as np
 import torch
@@ -16,25 +19,66 @@ from .engine import CLUSTER_DTYPE, Engine, require_cuda
 ARCH_NAME = "cuda/sm_100a"
 _SUPPORTED_ARCHS = (ARCH_NAME,)
 
-_engines = {}
+# Contexts are cached and reused (the reference rebuilds one per call, cfast_slic.pyx:171-197), in a small LRU:
+# a data set of variable-sized images must not pin one full context (~30 B/pixel of device memory) per shape
+# for ever.  Evicted contexts are closed; `Engine.lock` keeps a context another thread is using alive until
+# that call returns, and the cache itself is guarded by `_cache_lock`.
+ENGINE_CACHE_SIZE = 6
+_engines = collections.OrderedDict()
+_cache_lock = threading.Lock()
 
 
-def get_engine(H, W, K, batch=1, device=0):
-    """Contexts are cached and reused (the reference rebuilds one per call, cfast_slic.pyx:171-197)."""
-    key = (int(device), int(H), int(W), int(K))
-    eng = _engines.get(key)
-    if eng is None or eng.max_batch < batch:
-        if eng is not None:
-            eng.close()
-        eng = Engine(H, W, K, max_batch=batch, device=device)
-        _engines[key] = eng
+def _cached(key, make, min_batch):
+    with _cache_lock:
+        eng = _engines.get(key)
+        stale = []
+        if eng is not None and eng.max_batch < min_batch:
+            stale.append(_engines.pop(key))
+            eng = None
+        if eng is None:
+            eng = make()
+            _engines[key] = eng
+        _engines.move_to_end(key)
+        while len(_engines) > ENGINE_CACHE_SIZE:
+            stale.append(_engines.popitem(last=False)[1])
+    for e in stale:
+        e.close()  # takes e.lock: waits for a call in flight on another thread
     return eng
 
 
+def get_engine(H, W, K, batch=1, device=0):
+    key = ("slic", int(device), int(H), int(W), int(K))
+    return _cached(key, lambda: Engine(H, W, K, max_batch=batch, device=device), batch)
+
+
+def get_cca_engine(H, W, batch=1, device=0):
+    """Connectivity-only context: keyed on the shape alone (the label range K is a call argument)."""
+    key = ("cca", int(device), int(H), int(W))
+    return _cached(key, lambda: Engine(H, W, max_batch=batch, device=device, cca_only=True), batch)
+
+
+@contextlib.contextmanager
+def _locked(getter):
+    """The cached context of `getter()`, locked for the duration of the block.  If another thread evicted (and
+    closed) it between the lookup and the lock, look it up again."""
+    while True:
+        eng = getter()
+        eng.lock.acquire()
+        if eng._h is not None:
+            break
+        eng.lock.release()
+    try:
+        yield eng
+    finally:
+        eng.lock.release()
+
+
 def clear_engine_cache():
-    for e in _engines.values():
+    with _cache_lock:
+        engines = list(_engines.values())
+        _engines.clear()
+    for e in engines:
         e.close()
-    _engines.clear()
 
 
 def get_supported_archs():
@@ -152,8 +196,8 @@ class SlicModel(object):
         image = _check_image(image)
         require_cuda()
         H, W, _ = image.shape
-        eng = get_engine(H, W, self._num_components, 1, self.device)
-        self._clusters = eng.initialize_clusters_host(image[None])[0]
+        with _locked(lambda: get_engine(H, W, self._num_components, 1, self.device)) as eng:
+            self._clusters = eng.initialize_clusters_host(image[None])[0]
         self.initialized = True
 
     def iterate(self, image, max_iter, compactness, min_size_factor, subsample_stride):
@@ -164,13 +208,14 @@ class SlicModel(object):
         self._unsupported()
         require_cuda()
         H, W, _ = image.shape
-        eng = get_engine(H, W, self._num_components, 1, self.device)
-        params = eng.params(compactness, min_size_factor, subsample_stride, self.convert_to_lab, max_iter,
-                            collect_timing=1)
+        params = Engine.params(compactness, min_size_factor, subsample_stride, self.convert_to_lab, max_iter,
+                               collect_timing=1)
         clusters = np.ascontiguousarray(self._clusters)[None]
-        labels = eng.iterate_host(image[None], clusters, params)
+        # the lock covers the timing read-out too: it belongs to this call, not to another thread's next one
+        with _locked(lambda: get_engine(H, W, self._num_components, 1, self.device)) as eng:
+            labels = eng.iterate_host(image[None], clusters, params)
+            ms = eng.stage_ms()
         self._clusters = clusters[0]
-        ms = eng.stage_ms()
         self.last_timing_report = json.dumps({
             "name": "iterate", "duration": int(ms["iterate"] * 1000),
             "children": [{"name": n, "duration": int(ms[n] * 1000), "children": []}
@@ -245,20 +290,21 @@ class BaseSlic(object):
         if images.shape[3] != 3:
             raise ValueError("nchan != 3")
         device = images.device.index if is_tensor else self._slic_model.device
-        eng = get_engine(H, W, K, B, device)
-        params = eng.params(self.compactness, self.min_size_factor, self.subsample_stride, self.convert_to_lab,
-                            max_iter)
-        if is_tensor:
-            if clusters is None:
-                clusters = eng.initialize_clusters(images)
-            labels = eng.iterate(images, clusters, params)
-        else:
+        params = Engine.params(self.compactness, self.min_size_factor, self.subsample_stride, self.convert_to_lab,
+                               max_iter)
+        if not is_tensor:
             images = np.ascontiguousarray(images)
             if images.dtype != np.uint8:
                 raise ValueError("images must be uint8")
-            if clusters is None:
-                clusters = eng.initialize_clusters_host(images)
-            labels = eng.iterate_host(images, clusters, params)
+        with _locked(lambda: get_engine(H, W, K, B, device)) as eng:
+            if is_tensor:
+                if clusters is None:
+                    clusters = eng.initialize_clusters(images)
+                labels = eng.iterate(images, clusters, params)
+            else:
+                if clusters is None:
+                    clusters = eng.initialize_clusters_host(images)
+                labels = eng.iterate_host(images, clusters, params)
         return (labels, clusters) if return_clusters else labels
 
 
@@ -270,18 +316,22 @@ class Slic(BaseSlic):
 SlicCuda = Slic
 
 
-def enforce_connectivity(assignments, min_threshold):
-    """== cfast_slic.enforce_connectivity (cfast_slic.pyx:371-396): int16[H,W] in place, K = max label + 1."""
+def enforce_connectivity(assignments, min_threshold, device=0):
+    """== cfast_slic.enforce_connectivity (cfast_slic.pyx:371-396): int16[H,W] in place, K = max label + 1
+    (cfast_slic.pyx:377-382: the maximum over labels != -1).  K only bounds the number of kept components
+    (cca.cpp:176,225), so it may exceed H*W; the context is keyed on the shape alone."""
     if not isinstance(assignments, np.ndarray) or assignments.dtype != np.int16 or assignments.ndim != 2 \
             or not assignments.flags["C_CONTIGUOUS"]:
         raise ValueError("assignments must be a C-contiguous int16[H, W] array")
     require_cuda()
     H, W = assignments.shape
+    if H == 0 or W == 0:
+        return assignments
     lab = assignments.view(np.uint16)
     valid = lab[lab != 0xFFFF]
     K = (int(valid.max()) if valid.size else 0) + 1
-    eng = get_engine(H, W, max(min(K, 65533), 1), 1, 0)
-    t = torch.from_numpy(assignments).to(eng.device)[None].contiguous()
-    eng.enforce_connectivity(t, K, int(min_threshold))
-    assignments[...] = t[0].cpu().numpy()
+    with _locked(lambda: get_cca_engine(H, W, 1, device)) as eng:
+        t = torch.from_numpy(assignments).to(eng.device, non_blocking=False)[None].contiguous()
+        eng.enforce_connectivity(t, K, int(min_threshold))
+        assignments[...] = t[0].cpu().numpy()
     return assignments

@@ -26,6 +26,28 @@ static int set_err(int code, const std::string& msg) {
     g_err = msg;
     return code;
 }
+// Every entry point runs on the context's device and puts the caller's current device back on return
+// (a single-process multi-GPU PyTorch program must not find its current device changed behind its back).
+struct DeviceGuard {
+    int prev = -1;
+    bool changed = false;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) {
+            err = cudaSetDevice(dev);
+            changed = err == cudaSuccess;
+        }
+    }
+    ~DeviceGuard() {
+        if (changed) cudaSetDevice(prev);
+    }
+};
+#define USE_DEVICE(dev)                                                                               \
+    DeviceGuard dev_guard__(dev);                                                                     \
+    if (dev_guard__.err != cudaSuccess)                                                               \
+        return set_err(FSLIC_ECUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(dev_guard__.err))
+
 #define CK(call)                                                                                      \
     do {                                                                                              \
         cudaError_t e__ = (call);                                                                     \
@@ -35,6 +57,7 @@ static int set_err(int code, const std::string& msg) {
 
 struct fslic_ctx {
     int device = 0, H = 0, W = 0, K = 0, maxB = 0, S = 0, N = 0;
+    bool cca_only = false;  // fslic_b200_create_cca: connectivity scratch only
     int num_sms = 148;
     // tables
     uint16_t *d_gamma = nullptr, *d_labtbl = nullptr;
@@ -131,7 +154,7 @@ static cudaError_t dalloc(T** p, size_t count) {
 
 extern "C" int fslic_b200_destroy(fslic_ctx* c) {
     if (!c) return FSLIC_OK;
-    cudaSetDevice(c->device);
+    DeviceGuard dev_guard__(c->device);
     void* ptrs[] = {c->d_gamma, c->d_labtbl, c->quad,   c->labels,  c->cinfo,  c->acc,    c->cell_start,
                     c->cinfo_tmp, c->sptable, c->par,  c->aux,    c->cleader, c->carea,
                     c->cnew,    c->blkcnt, c->blkoff,  c->counters, c->ahist, c->heap, c->d_img,
@@ -155,7 +178,7 @@ extern "C" int fslic_b200_destroy(fslic_ctx* c) {
     return FSLIC_OK;
 }
 
-extern "C" int fslic_b200_create(int device, int H, int W, int K, int max_batch, fslic_ctx** out) {
+static int create_impl(int device, int H, int W, int K, int max_batch, bool cca_only, fslic_ctx** out) {
     if (!out) return set_err(FSLIC_EINVAL, "out is NULL");
     *out = nullptr;
     if (H <= 0 || W <= 0) return set_err(FSLIC_EINVAL, "H and W must be positive");
@@ -164,13 +187,14 @@ extern "C" int fslic_b200_create(int device, int H, int W, int K, int max_batch,
     if (max_batch <= 0) return set_err(FSLIC_EINVAL, "max_batch must be positive");
     if ((long)H * W >= (1L << 30)) return set_err(FSLIC_EINVAL, "image too large (H*W must be < 2^30)");
     if (H > 32767 || W > 32767) return set_err(FSLIC_EINVAL, "H and W must fit int16 (the reference truncates centres to int16)");
-    CK(cudaSetDevice(device));
+    USE_DEVICE(device);
     fslic_ctx* c = new (std::nothrow) fslic_ctx();
     if (!c) return set_err(FSLIC_ENOMEM, "out of host memory");
     c->device = device;
+    c->cca_only = cca_only;
     c->H = H; c->W = W; c->K = K; c->maxB = max_batch; c->N = H * W;
     c->S = (int)(int16_t)sqrt((double)(H * W / K));  // context.h:60 (integer division first)
-    if (c->S < 1) {  // the reference divides by zero here (PreemptiveGrid: ceil_int(W, 2*S), preemptive.h:37-38)
+    if (c->S < 1 && !cca_only) {  // the reference divides by zero here (PreemptiveGrid: ceil_int(W, 2*S), preemptive.h:37-38)
         delete c;
         return set_err(FSLIC_EINVAL, "num_components exceeds the number of pixels (S = 0): the reference crashes on this input");
     }
@@ -201,14 +225,16 @@ extern "C" int fslic_b200_create(int device, int H, int W, int K, int max_batch,
     while ((long)ceil_div(H, G) * ceil_div(W, G) > 16000) G++;
     c->G = G; c->cellW = ceil_div(W, G); c->cellH = ceil_div(H, G); c->ncell = c->cellW * c->cellH;
 
-    CKC(dalloc(&c->quad, B * N));
-    CKC(dalloc(&c->labels, B * N));
-    CKC(dalloc(&c->cinfo, B * K));
-    CKC(dalloc(&c->acc, B * K * 4));
-    CKC(cudaMemset(c->acc, 0, B * K * 4 * sizeof(unsigned long long)));
-    CKC(dalloc(&c->cell_start, B * (c->ncell + 1)));
-    CKC(dalloc(&c->cinfo_tmp, B * K));
-    CKC(dalloc(&c->sptable, (size_t)2 * SPT_MAX_ELEMS));
+    if (!cca_only) {  // assign state (a connectivity-only context needs none of it)
+        CKC(dalloc(&c->quad, B * N));
+        CKC(dalloc(&c->labels, B * N));
+        CKC(dalloc(&c->cinfo, B * K));
+        CKC(dalloc(&c->acc, B * K * 4));
+        CKC(cudaMemset(c->acc, 0, B * K * 4 * sizeof(unsigned long long)));
+        CKC(dalloc(&c->cell_start, B * (c->ncell + 1)));
+        CKC(dalloc(&c->cinfo_tmp, B * K));
+        CKC(dalloc(&c->sptable, (size_t)2 * SPT_MAX_ELEMS));
+    }
 
     // CCA scratch: 22 B/pixel/image; cap the resident set at ~12 GB
     const size_t per_img = N * 22 + 4096;
@@ -258,9 +284,19 @@ extern "C" int fslic_b200_create(int device, int H, int W, int K, int max_batch,
     return FSLIC_OK;
 }
 
-static int check_batch(fslic_ctx* c, int batch) {
+extern "C" int fslic_b200_create(int device, int H, int W, int K, int max_batch, fslic_ctx** out) {
+    return create_impl(device, H, W, K, max_batch, false, out);
+}
+
+extern "C" int fslic_b200_create_cca(int device, int H, int W, int max_batch, fslic_ctx** out) {
+    return create_impl(device, H, W, 1, max_batch, true, out);
+}
+
+static int check_batch(fslic_ctx* c, int batch, bool needs_assign_state = true) {
     if (!c) return set_err(FSLIC_EINVAL, "ctx is NULL");
     if (batch <= 0 || batch > c->maxB) return set_err(FSLIC_EINVAL, "batch out of range for this context");
+    if (needs_assign_state && c->cca_only)
+        return set_err(FSLIC_EINVAL, "this context was created by fslic_b200_create_cca: only enforce_connectivity is available");
     return FSLIC_OK;
 }
 
@@ -268,7 +304,7 @@ extern "C" int fslic_b200_initialize_clusters(fslic_ctx* c, const uint8_t* d_ima
                                               int batch, void* stream) {
     int rc = check_batch(c, batch);
     if (rc) return rc;
-    CK(cudaSetDevice(c->device));
+    USE_DEVICE(c->device);
     dim3 grid(ceil_div(c->K, 128), batch);
     k_init_clusters<<<grid, 128, 0, (cudaStream_t)stream>>>(d_images, d_clusters, c->H, c->W, c->K, batch);
     CK(cudaGetLastError());
@@ -291,7 +327,7 @@ extern "C" int fslic_b200_rgb_to_quad(fslic_ctx* c, const uint8_t* d_images, uin
                                       int convert_to_lab, void* stream) {
     int rc = check_batch(c, batch);
     if (rc) return rc;
-    CK(cudaSetDevice(c->device));
+    USE_DEVICE(c->device);
     return launch_lab(c, d_images, reinterpret_cast<uint32_t*>(d_quad_out), batch, convert_to_lab, (cudaStream_t)stream);
 }
 
@@ -413,10 +449,11 @@ static int run_cca(fslic_ctx* c, const uint16_t* d_in, uint16_t* d_out, int batc
 
 extern "C" int fslic_b200_enforce_connectivity(fslic_ctx* c, uint16_t* d_labels, int batch, int K, int min_threshold,
                                                void* stream) {
-    int rc = check_batch(c, batch);
+    int rc = check_batch(c, batch, false);
     if (rc) return rc;
     if (K <= 0) return FSLIC_OK;  // context.cpp:17
-    CK(cudaSetDevice(c->device));
+    if (K > 65535) return set_err(FSLIC_EINVAL, "K must fit the u16 label type");
+    USE_DEVICE(c->device);
     return run_cca(c, d_labels, d_labels, batch, K, min_threshold, (cudaStream_t)stream, nullptr);
 }
 
@@ -424,7 +461,7 @@ extern "C" int fslic_b200_debug_heap_select(fslic_ctx* c, const int32_t* d_area,
                                             void* stream) {
     if (!c) return set_err(FSLIC_EINVAL, "ctx is NULL");
     if (middle + 2 > c->heap_K || middle < 1 || n < 1) return set_err(FSLIC_EINVAL, "bad n/middle");
-    CK(cudaSetDevice(c->device));
+    USE_DEVICE(c->device);
     CK(cudaMemsetAsync(d_kept, 0, n, (cudaStream_t)stream));
     const size_t hb = (size_t)(2 * middle + 4) * 8;
     const int use_smem = hb + SEL_CHUNK * 8 <= (size_t)(c->max_smem_optin - 8 * 1024);
@@ -628,7 +665,7 @@ extern "C" int fslic_b200_iterate(fslic_ctx* c, const uint8_t* d_images, fslic_c
     float coef;
     rc = check_params(c, p, &coef);
     if (rc) return rc;
-    CK(cudaSetDevice(c->device));
+    USE_DEVICE(c->device);
     cudaStream_t st = (cudaStream_t)stream;
     int launches = 0;
     const bool timing = p->collect_timing != 0;
@@ -671,7 +708,7 @@ extern "C" int fslic_b200_assign_kernel_time(fslic_ctx* c, float* total_ms, int*
 
 extern "C" int fslic_b200_debug_cca_counters(fslic_ctx* c, int32_t* out8, int image) {
     if (!c || !out8 || image < 0 || image >= c->cca_batch) return set_err(FSLIC_EINVAL, "bad argument");
-    CK(cudaSetDevice(c->device));
+    USE_DEVICE(c->device);
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(out8, c->counters + image, sizeof(CcaCounters), cudaMemcpyDeviceToHost));
     return FSLIC_OK;
@@ -687,7 +724,7 @@ extern "C" int fslic_b200_debug_stages(fslic_ctx* c, uint8_t* d_quad_out, uint16
                                        void* stream) {
     int rc = check_batch(c, batch);
     if (rc) return rc;
-    CK(cudaSetDevice(c->device));
+    USE_DEVICE(c->device);
     cudaStream_t st = (cudaStream_t)stream;
     if (d_quad_out) CK(cudaMemcpyAsync(d_quad_out, c->quad, (size_t)batch * c->N * 4, cudaMemcpyDeviceToDevice, st));
     if (d_precca_out) CK(cudaMemcpyAsync(d_precca_out, c->labels, (size_t)batch * c->N * 2, cudaMemcpyDeviceToDevice, st));
@@ -696,11 +733,25 @@ extern "C" int fslic_b200_debug_stages(fslic_ctx* c, uint8_t* d_quad_out, uint16
 
 // ---- host-buffer entry points (what the reference-facing plugin calls) --------------------------
 static int ensure_staging(fslic_ctx* c) {
-    if (c->d_img) return FSLIC_OK;
+    if (c->d_img && c->d_cl && c->d_lab) return FSLIC_OK;
     const size_t B = (size_t)c->maxB, N = (size_t)c->N;
-    CK(dalloc(&c->d_img, B * N * 3));
-    CK(dalloc(&c->d_cl, B * c->K));
-    CK(dalloc(&c->d_lab, B * N));
+    // allocate into temporaries and commit all three together: a failed second or third allocation must not
+    // leave a half-initialised staging set behind for the next call to trip over
+    uint8_t* img = nullptr;
+    fslic_cluster* cl = nullptr;
+    uint16_t* lab = nullptr;
+    cudaError_t e = dalloc(&img, B * N * 3);
+    if (e == cudaSuccess) e = dalloc(&cl, B * c->K);
+    if (e == cudaSuccess) e = dalloc(&lab, B * N);
+    if (e != cudaSuccess) {
+        if (img) cudaFree(img);
+        if (cl) cudaFree(cl);
+        if (lab) cudaFree(lab);
+        cudaGetLastError();
+        return set_err(e == cudaErrorMemoryAllocation ? FSLIC_ENOMEM : FSLIC_ECUDA,
+                       std::string("staging buffers: ") + cudaGetErrorString(e));
+    }
+    c->d_img = img; c->d_cl = cl; c->d_lab = lab;
     return FSLIC_OK;
 }
 
@@ -708,7 +759,7 @@ extern "C" int fslic_b200_initialize_clusters_host(fslic_ctx* c, const uint8_t* 
                                                    int batch) {
     int rc = check_batch(c, batch);
     if (rc) return rc;
-    CK(cudaSetDevice(c->device));
+    USE_DEVICE(c->device);
     rc = ensure_staging(c);
     if (rc) return rc;
     cudaStream_t st = c->own_stream;
@@ -767,11 +818,11 @@ static int iterate_graphed(fslic_ctx* c, const uint8_t* d_images, fslic_cluster*
 // Enqueues H2D -> kernels -> D2H for one host batch on the context's three streams.  With may_sync the caller is
 // going to block anyway, so the connectivity stage may read its per-image decisions back mid-way and start the
 // label download of settled images early; without it nothing here waits for the device.
-static int iterate_host_enqueue(fslic_ctx* c, const uint8_t* h_images, fslic_cluster* h_clusters, uint16_t* h_labels,
-                                int batch, const fslic_params* p, bool may_sync) {
+static int iterate_host_enqueue_body(fslic_ctx* c, const uint8_t* h_images, fslic_cluster* h_clusters,
+                                     uint16_t* h_labels, int batch, const fslic_params* p, bool may_sync) {
     int rc = check_batch(c, batch);
     if (rc) return rc;
-    CK(cudaSetDevice(c->device));
+    USE_DEVICE(c->device);
     rc = ensure_staging(c);
     if (rc) return rc;
     if (c->pending) {  // one batch in flight per context: its staging buffers are about to be overwritten
@@ -891,6 +942,25 @@ static int iterate_host_enqueue(fslic_ctx* c, const uint8_t* h_images, fslic_clu
     return FSLIC_OK;
 }
 
+static int iterate_host_enqueue(fslic_ctx* c, const uint8_t* h_images, fslic_cluster* h_clusters, uint16_t* h_labels,
+                                int batch, const fslic_params* p, bool may_sync) {
+    const int rc = iterate_host_enqueue_body(c, h_images, h_clusters, h_labels, batch, p, may_sync);
+    if (rc != FSLIC_OK && c && c->in_stream) {
+        // an error after copies / kernels were enqueued: nothing may stay in flight on the staging buffers or the
+        // caller's host buffers once the error is reported
+        const std::string keep = g_err;
+        DeviceGuard g(c->device);
+        cudaStreamSynchronize(c->in_stream);
+        cudaStreamSynchronize(c->own_stream);
+        cudaStreamSynchronize(c->side_stream);
+        cudaStreamSynchronize(c->out_stream);
+        cudaGetLastError();
+        c->pending = false;
+        g_err = keep;
+    }
+    return rc;
+}
+
 extern "C" int fslic_b200_iterate_host(fslic_ctx* c, const uint8_t* h_images, fslic_cluster* h_clusters,
                                        uint16_t* h_labels, int batch, const fslic_params* p) {
     return iterate_host_enqueue(c, h_images, h_clusters, h_labels, batch, p, true);
@@ -904,7 +974,7 @@ extern "C" int fslic_b200_iterate_host_async(fslic_ctx* c, const uint8_t* h_imag
 extern "C" int fslic_b200_wait(fslic_ctx* c) {
     if (!c) return set_err(FSLIC_EINVAL, "ctx is NULL");
     if (!c->pending) return FSLIC_OK;
-    CK(cudaSetDevice(c->device));
+    USE_DEVICE(c->device);
     CK(cudaStreamSynchronize(c->out_stream));
     CK(cudaStreamSynchronize(c->own_stream));
     c->pending = false;

@@ -4,6 +4,7 @@ Host logic only -- tensors in, tensors out; all arithmetic happens in libfslic_b
 PyTorch is used for device memory and streams, nothing else.
 """
 import ctypes as C
+import threading
 
 import numpy as np
 import torch
@@ -28,20 +29,30 @@ def require_cuda():
 
 
 class Engine:
-    def __init__(self, H, W, K, max_batch=1, device=0):
+    """A context is NOT safe for concurrent calls (shared staging buffers, streams, graph key).
+    `lock` serialises them: every blocking entry point below holds it for the whole call, and callers that pair
+    `iterate_host_async` with `wait` from several threads must hold it across the pair themselves."""
+
+    def __init__(self, H, W, K=None, max_batch=1, device=0, cca_only=False):
         require_cuda()
-        self.H, self.W, self.K, self.max_batch = int(H), int(W), int(K), int(max_batch)
+        self.cca_only = bool(cca_only)
+        self.H, self.W, self.K, self.max_batch = int(H), int(W), (1 if cca_only else int(K)), int(max_batch)
         self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
         self._L = _lib.lib()
+        self.lock = threading.RLock()
         h = C.c_void_p()
-        check(self._L.fslic_b200_create(self.device.index, self.H, self.W, self.K, self.max_batch, C.byref(h)))
+        if cca_only:  # scratch of the connectivity stage alone; K is an argument of enforce_connectivity()
+            check(self._L.fslic_b200_create_cca(self.device.index, self.H, self.W, self.max_batch, C.byref(h)))
+        else:
+            check(self._L.fslic_b200_create(self.device.index, self.H, self.W, self.K, self.max_batch, C.byref(h)))
         self._h = h
         self.S = self._L.fslic_b200_get_S(self._h)
 
     def close(self):
-        if getattr(self, "_h", None):
-            self._L.fslic_b200_destroy(self._h)
-            self._h = None
+        with self.lock:
+            if getattr(self, "_h", None):
+                self._L.fslic_b200_destroy(self._h)
+                self._h = None
 
     def __del__(self):
         try:
@@ -75,8 +86,9 @@ class Engine:
         B = images.shape[0]
         if clusters is None:
             clusters = self.new_clusters(B)
-        check(self._L.fslic_b200_initialize_clusters(self._h, images.data_ptr(), clusters.data_ptr(), B,
-                                                     _stream_ptr(self.device)))
+        with self.lock:
+            check(self._L.fslic_b200_initialize_clusters(self._h, images.data_ptr(), clusters.data_ptr(), B,
+                                                         _stream_ptr(self.device)))
         return clusters
 
     def iterate(self, images, clusters, params, labels=None):
@@ -85,15 +97,17 @@ class Engine:
         B = images.shape[0]
         if labels is None:
             labels = torch.empty((B, self.H, self.W), dtype=torch.int16, device=self.device)
-        check(self._L.fslic_b200_iterate(self._h, images.data_ptr(), clusters.data_ptr(), labels.data_ptr(), B,
-                                         C.byref(params), _stream_ptr(self.device)))
+        with self.lock:
+            check(self._L.fslic_b200_iterate(self._h, images.data_ptr(), clusters.data_ptr(), labels.data_ptr(), B,
+                                             C.byref(params), _stream_ptr(self.device)))
         return labels
 
     def enforce_connectivity(self, labels, K, min_threshold):
         """In place on int16/uint16 labels [B,H,W] (cuda)."""
         B = labels.shape[0]
-        check(self._L.fslic_b200_enforce_connectivity(self._h, labels.data_ptr(), B, int(K), int(min_threshold),
-                                                      _stream_ptr(self.device)))
+        with self.lock:
+            check(self._L.fslic_b200_enforce_connectivity(self._h, labels.data_ptr(), B, int(K), int(min_threshold),
+                                                          _stream_ptr(self.device)))
         return labels
 
     def rgb_to_quad(self, images, convert_to_lab=True):
@@ -122,15 +136,17 @@ class Engine:
     def initialize_clusters_host(self, images_np):
         B = images_np.shape[0]
         clusters = np.zeros((B, self.K), CLUSTER_DTYPE)
-        check(self._L.fslic_b200_initialize_clusters_host(self._h, images_np.ctypes.data, clusters.ctypes.data, B))
+        with self.lock:
+            check(self._L.fslic_b200_initialize_clusters_host(self._h, images_np.ctypes.data, clusters.ctypes.data, B))
         return clusters
 
     def iterate_host(self, images_np, clusters_np, params, labels_np=None):
         B = images_np.shape[0]
         if labels_np is None:
             labels_np = np.empty((B, self.H, self.W), np.int16)
-        check(self._L.fslic_b200_iterate_host(self._h, images_np.ctypes.data, clusters_np.ctypes.data,
-                                              labels_np.ctypes.data, B, C.byref(params)))
+        with self.lock:
+            check(self._L.fslic_b200_iterate_host(self._h, images_np.ctypes.data, clusters_np.ctypes.data,
+                                                  labels_np.ctypes.data, B, C.byref(params)))
         return labels_np
 
     def iterate_host_async(self, images_np, clusters_np, params, labels_np):

@@ -73,6 +73,11 @@ int fslic_b200_sizeof_cluster(void);
 int fslic_b200_create(int device, int H, int W, int K, int max_batch, fslic_ctx** out);
 int fslic_b200_destroy(fslic_ctx* ctx);
 
+/* == the scratch of cca::ConnectivityEnforcer alone (cca.cpp:176-192: it needs H, W and nothing of the SLIC
+ *    context): a context on which only fslic_b200_enforce_connectivity may be called.  No K is fixed here --
+ *    K (max_label_size) is an argument of that call, exactly like the reference's constructor argument. */
+int fslic_b200_create_cca(int device, int H, int W, int max_batch, fslic_ctx** out);
+
 /* == BaseContext::initialize_clusters (context.cpp:43-97), for `batch` images [B,H,W,3] u8. */
 int fslic_b200_initialize_clusters(fslic_ctx* ctx, const uint8_t* d_images, fslic_cluster* d_clusters, int batch,
                                    void* stream);

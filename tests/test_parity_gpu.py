@@ -34,13 +34,13 @@ def _run_cuda(img, K, args, iterate_twice=False):
         cl[0].cpu().numpy()
 
 
-def _run_oracle(port, img, K, args, iterate_twice=False):
-    cl = port.initialize(img, K)
+def _run_oracle(checker, img, K, args, iterate_twice=False):
+    cl = checker.initialize(img, K)
     init = cl.copy()
-    out, quad, pre = port.iterate(img, cl, args["max_iter"], args["compactness"], args["min_size_factor"],
+    out, quad, pre = checker.iterate(img, cl, args["max_iter"], args["compactness"], args["min_size_factor"],
                                   args["subsample_stride"], args["convert_to_lab"], stages=True)
     if iterate_twice:
-        out, quad, pre = port.iterate(img, cl, args["max_iter"], args["compactness"], args["min_size_factor"],
+        out, quad, pre = checker.iterate(img, cl, args["max_iter"], args["compactness"], args["min_size_factor"],
                                       args["subsample_stride"], args["convert_to_lab"], stages=True)
     return init, out, quad, pre, cl
 
@@ -58,19 +58,19 @@ def _compare(name, got, want):
 
 
 @pytest.mark.parametrize("case", PIPELINE_CASES, ids=[c[0] for c in PIPELINE_CASES])
-def test_pipeline_parity(port, case):
+def test_pipeline_parity(checker, case):
     name, kind, H, W, K, kw = case
     sigma, args = split_kwargs(kw)
     img = make_image(kind, H, W, seed=7, sigma=sigma)
-    _compare(name, _run_cuda(img, K, args), _run_oracle(port, img, K, args))
+    _compare(name, _run_cuda(img, K, args), _run_oracle(checker, img, K, args))
 
 
 @pytest.mark.parametrize("case", EDGE_CASES, ids=[c[0] for c in EDGE_CASES])
-def test_pipeline_parity_edge(port, case):
+def test_pipeline_parity_edge(checker, case):
     name, kind, H, W, K, kw = case
     sigma, args = split_kwargs(kw)
     img = make_image(kind, H, W, seed=5, sigma=sigma)
-    _compare(name, _run_cuda(img, K, args), _run_oracle(port, img, K, args))
+    _compare(name, _run_cuda(img, K, args), _run_oracle(checker, img, K, args))
 
 
 def test_rejects_what_the_reference_cannot_do():
@@ -84,20 +84,20 @@ def test_rejects_what_the_reference_cannot_do():
 
 
 @pytest.mark.parametrize("case", BIG_CASES, ids=[c[0] for c in BIG_CASES])
-def test_pipeline_parity_big(port, case):
+def test_pipeline_parity_big(checker, case):
     name, kind, H, W, K, kw = case
     sigma, args = split_kwargs(kw)
     img = make_image(kind, H, W, seed=11, sigma=sigma)
-    _compare(name, _run_cuda(img, K, args), _run_oracle(port, img, K, args))
+    _compare(name, _run_cuda(img, K, args), _run_oracle(checker, img, K, args))
 
 
-def test_warm_start_second_iterate(port):
+def test_warm_start_second_iterate(checker):
     img = make_image("syn", 200, 260, seed=3)
     _, args = split_kwargs({})
-    _compare("warm", _run_cuda(img, 90, args, iterate_twice=True), _run_oracle(port, img, 90, args, iterate_twice=True))
+    _compare("warm", _run_cuda(img, 90, args, iterate_twice=True), _run_oracle(checker, img, 90, args, iterate_twice=True))
 
 
-def test_batch_matches_single(port):
+def test_batch_matches_single(checker):
     H, W, K, B = 180, 240, 70, 5
     imgs = np.stack([make_image("syn" if b % 2 == 0 else "noise", H, W, seed=20 + b) for b in range(B)])
     from fast_slic_b200 import Slic
@@ -106,14 +106,14 @@ def test_batch_matches_single(port):
     labels = labels.cpu().numpy().view(np.uint16)
     labels_h, clusters_h = s.iterate_batch(imgs, return_clusters=True)
     for b in range(B):
-        cl = port.initialize(imgs[b], K)
-        want = port.iterate(imgs[b], cl, 10, 10.0, 0.1, 3, True)
+        cl = checker.initialize(imgs[b], K)
+        want = checker.iterate(imgs[b], cl, 10, 10.0, 0.1, 3, True)
         assert (labels[b] == want).all(), "device batch image %d" % b
         assert (labels_h[b].view(np.uint16) == want).all(), "host batch image %d" % b
         assert clusters[b].cpu().numpy().tobytes() == cl.tobytes() == clusters_h[b].tobytes()
 
 
-def test_sub_batched_paths(port, monkeypatch):
+def test_sub_batched_paths(checker, monkeypatch):
     """Forces the CCA sub-batch loop (scratch smaller than the batch) and the multi-chunk host pipeline."""
     from fast_slic_b200 import Slic, clear_engine_cache
     monkeypatch.setenv("FSLIC_CCA_BATCH", "2")
@@ -126,14 +126,14 @@ def test_sub_batched_paths(port, monkeypatch):
         lab_d = s.iterate_batch(torch.from_numpy(imgs).cuda()).cpu().numpy().view(np.uint16)
         lab_h = s.iterate_batch(imgs).view(np.uint16)
         for b in range(B):
-            cl = port.initialize(imgs[b], K)
-            want = port.iterate(imgs[b], cl, 10, 10.0, 0.0, 3, True)
+            cl = checker.initialize(imgs[b], K)
+            want = checker.iterate(imgs[b], cl, 10, 10.0, 0.0, 3, True)
             assert (lab_d[b] == want).all() and (lab_h[b] == want).all(), b
     finally:
         clear_engine_cache()
 
 
-def test_streaming_matches_blocking(port):
+def test_streaming_matches_blocking(checker):
     """SlicStream (iterate_host_async / wait on two alternating contexts) == the oracle, batch by batch, with
     pinned and pageable inputs, ragged last batch and more batches than slots."""
     from fast_slic_b200 import SlicStream
@@ -149,21 +149,21 @@ def test_streaming_matches_blocking(port):
     for t, labs in enumerate(got):
         assert labs.shape == (batches[t].shape[0], H, W)
         for b in range(labs.shape[0]):
-            cl = port.initialize(batches[t][b], K)
-            want = port.iterate(batches[t][b], cl, 10, 10.0, 0.0, 3, True)
+            cl = checker.initialize(batches[t][b], K)
+            want = checker.iterate(batches[t][b], cl, 10, 10.0, 0.0, 3, True)
             assert (labs[b].view(np.uint16) == want).all(), (t, b)
     # explicit submit / collect: clusters come back too, and over-submitting is refused
     st.submit(batches[0]); st.submit(batches[2])
     with pytest.raises(RuntimeError):
         st.submit(batches[3])
     labs, cls = st.collect()
-    cl = port.initialize(batches[0][1], K)
-    want = port.iterate(batches[0][1], cl, 10, 10.0, 0.0, 3, True)
+    cl = checker.initialize(batches[0][1], K)
+    want = checker.iterate(batches[0][1], cl, 10, 10.0, 0.0, 3, True)
     assert (labs[1].view(np.uint16) == want).all() and cls[1].tobytes() == cl.tobytes()
     st.close()
 
 
-def test_async_same_context_serialises(port):
+def test_async_same_context_serialises(checker):
     """Two _async calls on ONE context: the second waits for the first instead of overwriting its staging."""
     from fast_slic_b200 import Engine, CLUSTER_DTYPE
     H, W, K, B = 96, 128, 30, 3
@@ -181,14 +181,14 @@ def test_async_same_context_serialises(port):
     eng.wait()  # idempotent
     for imgs, cl, lab in bufs:
         for b in range(B):
-            c0 = port.initialize(imgs.numpy()[b], K)
-            want = port.iterate(imgs.numpy()[b], c0, 10, 10.0, 0.1, 3, True)
+            c0 = checker.initialize(imgs.numpy()[b], K)
+            want = checker.iterate(imgs.numpy()[b], c0, 10, 10.0, 0.1, 3, True)
             assert (lab.numpy()[b].view(np.uint16) == want).all()
             assert cl.numpy()[b].tobytes() == c0.tobytes()
     eng.close()
 
 
-def test_graph_replay_small_host_batches(port, monkeypatch):
+def test_graph_replay_small_host_batches(checker, monkeypatch):
     """Host calls with fewer than 4 images replay one captured CUDA graph (default; FSLIC_GRAPH=0 disables).  Same
     results as the plain launches for changing images (replay), changing parameters (re-capture) and the async entry point."""
     from fast_slic_b200 import Engine
@@ -202,8 +202,8 @@ def test_graph_replay_small_host_batches(port, monkeypatch):
             cl = eng.initialize_clusters_host(imgs)
             lab = eng.iterate_host(imgs, cl, p)
             for b in range(2):
-                c0 = port.initialize(imgs[b], K)
-                want = port.iterate(imgs[b], c0, 10, 10.0, msf, 3, True)
+                c0 = checker.initialize(imgs[b], K)
+                want = checker.iterate(imgs[b], c0, 10, 10.0, msf, 3, True)
                 assert (lab[b].view(np.uint16) == want).all(), (msf, t, b)
                 assert cl[b].tobytes() == c0.tobytes()
     # one image, async entry point, same context: a third graph
@@ -214,8 +214,8 @@ def test_graph_replay_small_host_batches(port, monkeypatch):
         lab = torch.empty((1, H, W), dtype=torch.int16).pin_memory()
         eng.iterate_host_async(img.numpy(), cl.numpy(), p, lab.numpy())
         eng.wait()
-        c0 = port.initialize(img.numpy()[0], K)
-        want = port.iterate(img.numpy()[0], c0, 10, 10.0, 0.1, 3, True)
+        c0 = checker.initialize(img.numpy()[0], K)
+        want = checker.iterate(img.numpy()[0], c0, 10, 10.0, 0.1, 3, True)
         assert (lab.numpy()[0].view(np.uint16) == want).all() and cl.numpy()[0].tobytes() == c0.tobytes()
     eng.close()
 
@@ -262,7 +262,7 @@ def test_enforce_connectivity_known_answer():
 @pytest.mark.parametrize("H,W,nlab,thres,seed", [(60, 80, 6, 0, 1), (60, 80, 6, 5, 2), (100, 33, 3, 12, 3),
                                                  (257, 515, 40, 30, 4), (64, 64, 2, 1, 5), (1, 700, 4, 3, 6),
                                                  (700, 1, 4, 3, 7), (720, 1280, 1600, 58, 8)])
-def test_enforce_connectivity_random(port, H, W, nlab, thres, seed):
+def test_enforce_connectivity_random(checker, H, W, nlab, thres, seed):
     from fast_slic_b200 import enforce_connectivity
     rng = np.random.RandomState(seed)
     small = rng.randint(0, nlab, (H // 3 + 1, W // 3 + 1))
@@ -271,9 +271,38 @@ def test_enforce_connectivity_random(port, H, W, nlab, thres, seed):
     lab[noise] = rng.randint(0, nlab, noise.sum())
     lab = np.ascontiguousarray(lab.astype(np.int16))
     K = int(lab.max()) + 1
-    want = port.enforce_connectivity(lab.view(np.uint16), K, thres)
+    want = checker.enforce_connectivity(lab.view(np.uint16), K, thres)
     got = enforce_connectivity(lab.copy(), thres).view(np.uint16)
     assert (got == want).all(), "%d px differ" % (got != want).sum()
+
+
+def test_enforce_connectivity_label_range_beyond_pixel_count(checker):
+    """a small crop with large label ids (K = max label + 1 > H*W) is legal for the reference's
+    ConnectivityEnforcer (K only bounds the kept set, cca.cpp:176,225); varying K must not build new contexts."""
+    from fast_slic_b200 import base_slic, enforce_connectivity
+    rng = np.random.RandomState(77)
+    for trial, (H, W, top) in enumerate([(50, 50, 4000), (50, 50, 65000), (50, 50, 37), (9, 13, 30000)]):
+        small = rng.randint(0, 12, (H // 4 + 1, W // 4 + 1))
+        lab = np.kron(small, np.ones((4, 4), int))[:H, :W]
+        ids = np.sort(rng.choice(top, 12, replace=False))
+        ids[-1] = top  # the maximum label is `top`
+        lab = np.ascontiguousarray(ids[lab].astype(np.uint16).view(np.int16))
+        K = top + 1
+        want = checker.enforce_connectivity(lab.view(np.uint16), K, 3)
+        got = enforce_connectivity(lab.copy(), 3).view(np.uint16)
+        assert (got == want).all(), "trial %d: %d px differ" % (trial, (got != want).sum())
+    assert sum(1 for k in base_slic._engines if k[0] == "cca" and k[2:] == (50, 50)) == 1
+
+
+def test_engine_cache_is_bounded():
+    from fast_slic_b200 import base_slic, get_engine
+    base_slic.clear_engine_cache()
+    first = get_engine(40, 40, 5)
+    for i in range(base_slic.ENGINE_CACHE_SIZE + 3):
+        get_engine(40 + 8 * (i + 1), 48, 6)
+    assert len(base_slic._engines) == base_slic.ENGINE_CACHE_SIZE
+    assert first._h is None  # evicted contexts are closed, not leaked
+    base_slic.clear_engine_cache()
 
 
 def test_python_surface_matches_reference_api():
@@ -299,15 +328,15 @@ def test_python_surface_matches_reference_api():
     assert rep["name"] == "iterate" and len(rep["children"]) == 5
 
 
-def test_single_image_api_parity(port):
+def test_single_image_api_parity(checker):
     from fast_slic_b200 import Slic
     img = make_image("syn", 240, 320, seed=5)
     s = Slic(num_components=120, min_size_factor=0.1)
     got = s.iterate(img).view(np.uint16)
-    cl = port.initialize(img, 120)
-    want = port.iterate(img, cl, 10, 10.0, 0.1, 3, True)
+    cl = checker.initialize(img, 120)
+    want = checker.iterate(img, cl, 10, 10.0, 0.1, 3, True)
     assert (got == want).all()
     assert s.slic_model.cluster_array.tobytes() == cl.tobytes()
     got2 = s.iterate(img).view(np.uint16)  # warm start
-    want2 = port.iterate(img, cl, 10, 10.0, 0.1, 3, True)
+    want2 = checker.iterate(img, cl, 10, 10.0, 0.1, 3, True)
     assert (got2 == want2).all()
