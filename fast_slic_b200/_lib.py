@@ -17,6 +17,7 @@ EXPORTED_SYMBOLS = (
     "fslic_b200_rgb_to_quad", "fslic_b200_debug_heap_select", "fslic_b200_stage_ms", "fslic_b200_get_S",
     "fslic_b200_launches_last_iterate", "fslic_b200_assign_kernel_time", "fslic_b200_debug_cca_counters",
     "fslic_b200_iterate_host_async", "fslic_b200_wait", "fslic_b200_create_cca",
+    "fslic_b200_debug_assign_impl",
 )
 
 STAGE_NAMES = ("cielab_conversion", "assign", "update", "full_assign", "enforce_connectivity", "iterate")
@@ -70,6 +71,7 @@ def lib():
     L.fslic_b200_stage_ms.argtypes = [vp, C.POINTER(C.c_float), i32]
     L.fslic_b200_get_S.argtypes = [vp]
     L.fslic_b200_launches_last_iterate.argtypes = [vp]
+    L.fslic_b200_debug_assign_impl.argtypes = [vp]
     L.fslic_b200_assign_kernel_time.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
     L.fslic_b200_debug_cca_counters.argtypes = [vp, C.POINTER(C.c_int32), i32]
     assert L.fslic_b200_sizeof_cluster() == 32

@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(AS_THREADS, AS_MINB) k_assign_warp(AssignParam
                                                                unsigned long long* __restrict__ acc,
                                                                const uint16_t* __restrict__ g_tbl) {
     constexpr int R = AS_R;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     uint16_t* s_tbl = reinterpret_cast<uint16_t*>(smem_raw);
     // per-warp private staging block behind the patch in dynamic shared memory (AS_STAGE_BYTES in total):
     //   [ent: AS_T x 32 x uint2][ukey: AS_T x 32 x u32][ucol: same][ucyx: same][k: AS_T x 32 x u16]

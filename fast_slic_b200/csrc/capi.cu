@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "assign.cuh"
+#include "assign5.cuh"
 #include "cca.cuh"
 #include "common.cuh"
 #include "lab.cuh"
@@ -20,6 +21,10 @@
 typedef void (*assign_fn)(AssignParams, const uint32_t*, uint16_t*, const CInfo*, const int*, unsigned long long*,
                           const uint16_t*);
 static assign_fn pick_assign(int TS, int stride, bool update);
+
+typedef void (*assign5_fn)(AssignParams, const CUtensorMap, const CUtensorMap, const uint32_t*, uint16_t*, const CInfo*,
+                           const int*, unsigned long long*, const uint16_t*);
+static assign5_fn pick_assign5(int TS, bool update, int tps);
 
 static thread_local std::string g_err;
 static int set_err(int code, const std::string& msg) {
@@ -116,6 +121,8 @@ struct fslic_ctx {
     int glaunches = 0;
     float assign_kernel_ms = 0.f;
     int assign_kernel_launches = 0;
+    int assign_impl = 5;       // 5: TMA-staged kernel where it applies (default), 4: always the LDG kernel (FSLIC_ASSIGN=4)
+    int last_assign_impl = 0;  // which kernel the last subsampled / full pass used (tests, bench)
 };
 
 extern "C" const char* fslic_b200_last_error(void) { return g_err.c_str(); }
@@ -123,6 +130,7 @@ extern "C" const char* fslic_b200_version(void) { return "fast_slic_b200 0.1 (sm
 extern "C" int fslic_b200_sizeof_cluster(void) { return (int)sizeof(fslic_cluster); }
 extern "C" int fslic_b200_get_S(const fslic_ctx* ctx) { return ctx ? ctx->S : -1; }
 extern "C" int fslic_b200_launches_last_iterate(const fslic_ctx* ctx) { return ctx ? ctx->last_launches : -1; }
+extern "C" int fslic_b200_debug_assign_impl(const fslic_ctx* ctx) { return ctx ? ctx->last_assign_impl : -1; }
 
 // ---- Lab tables: FastCIELabCvt ctor, /root/reference/src/cielab.h:297-305 ----------------------
 // _srgb_gamma_tbl (cielab.h:22-279) is the sRGB inverse companding curve documented at
@@ -277,6 +285,12 @@ static int create_impl(int device, int H, int W, int K, int max_batch, bool cca_
             for (int upd = 0; upd < 2; upd++)
                 CKC(cudaFuncSetAttribute(pick_assign(ts, stride, upd != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          c->max_smem_optin - 1024));
+    for (int ts : {128, 192, 256})
+        for (int upd = 0; upd < 2; upd++)
+            for (int tps : {1, 4})
+                CKC(cudaFuncSetAttribute(pick_assign5(ts, upd != 0, tps), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         c->max_smem_optin - 1024));
+    if (const char* e = getenv("FSLIC_ASSIGN")) c->assign_impl = atoi(e) == 4 ? 4 : 5;
     CKC(cudaFuncSetAttribute(k_cca_select, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin - 4 * 1024));
     CKC(cudaFuncSetAttribute(k_debug_heap_select, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin - 4 * 1024));
     CKC(cudaFuncSetAttribute(k_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
@@ -517,6 +531,54 @@ static assign_fn pick_assign(int TS, int stride, bool update) {
     }
 }
 
+// kernel menu of the TMA-staged kernel: TS in {128,192,256} x (stride 3 + update | stride 1, no update) x TPS in {1,4}
+template <int TS>
+static assign5_fn pick_assign5_ts(bool update, int tps) {
+    if (update) return tps == 4 ? k_assign5<TS, 3, true, 4> : k_assign5<TS, 3, true, 1>;
+    return tps == 4 ? k_assign5<TS, 1, false, 4> : k_assign5<TS, 1, false, 1>;
+}
+static assign5_fn pick_assign5(int TS, bool update, int tps) {
+    switch (TS) {
+        case 128: return pick_assign5_ts<128>(update, tps);
+        case 192: return pick_assign5_ts<192>(update, tps);
+        default: return pick_assign5_ts<256>(update, tps);
+    }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point table (no link against libcuda)
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static encode_tiled_fn tensor_map_encoder() {
+    static encode_tiled_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<encode_tiled_fn>(p);
+        cudaGetLastError();
+    }
+    return fn;
+}
+
+// 3-D view (x, sub-row, image) of the rows i = rem + sr * stride of a [B][H][W] array of `esize`-byte pixels;
+// box = box_w columns x 4 sub-rows x 1 image.  Out-of-range parts of a box read as zero and are not written.
+static bool make_subrow_map(CUtensorMap* m, CUtensorMapDataType dt, int esize, void* base, int H, int W, int B, int stride,
+                            int rem, int nsub, int box_w) {
+    encode_tiled_fn enc = tensor_map_encoder();
+    if (!enc) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)nsub, (cuuint64_t)B};
+    const cuuint64_t strides[2] = {(cuuint64_t)stride * W * esize, (cuuint64_t)H * W * esize};
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, 4u, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    unsigned char* p = static_cast<unsigned char*>(base) + (size_t)rem * W * esize;
+    return enc(m, dt, 3, p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static int build_patches(fslic_ctx* c, int stride, bool need_sub, float coef, cudaStream_t st, int* launches) {
     if (need_sub) {
         const PassGeom g = pass_geometry(c, stride);
@@ -551,7 +613,63 @@ static int run_assign_pass(fslic_ctx* c, int batch, int stride, int rem, int cfg
     ap.ntiles = ap.tiles_x * ap.tiles_y;
     ap.coef = coef;
     ap.tps = AS_T;
-    if (g.fast) {
+    // The TMA-staged kernel: row strides of the tensor maps must be multiples of 16 bytes (W % 8 == 0 for the u16
+    // labels), the sub-row pitch is an immediate of its patch loads (stride 3 with the update, 1 without), and its
+    // per-warp shared blocks must fit beside the patch.  Everything else takes the LDG kernel below.
+    bool use5 = g.fast && c->assign_impl == 5 && (c->W % 8) == 0 && g.TS <= 256 && (update ? stride == 3 : stride == 1) &&
+                tensor_map_encoder() != nullptr;
+    int warps5 = 0;
+    size_t smem5 = 0;
+    if (use5) {
+        const size_t tblb = align_up((size_t)g.tbl_elems * 2, 128);
+        for (int w : {32, 16, 8}) {
+            smem5 = tblb + (size_t)w * A5_WBLK + (size_t)w * 8;
+            if (smem5 <= (size_t)(c->max_smem_optin - 1024)) {
+                warps5 = w;
+                break;
+            }
+        }
+        if (!warps5) use5 = false;
+    }
+    if (use5) {
+        // super tiles of 4 tiles when that still gives every warp of the grid work and the union list stays well below
+        // its 32 slots; single tiles otherwise (single images, small S)
+        const double est4 = (double)(2 * c->S + stride * 3 + 1) * (2 * c->S + 128) / ((double)c->S * c->S);
+        const long supers4 = (long)ceil_div(ap.tiles_x, 4) * ap.tiles_y * batch;
+        const int tps = (est4 <= 24.0 && supers4 >= (long)c->num_sms * warps5) ? 4 : 1;
+        ap.tps = tps;
+        CUtensorMap tmq, tml;
+        uint32_t* qbase = SL_QUAD(c);
+        uint16_t* lbase = SL_LABELS(c);
+        if (!make_subrow_map(&tmq, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, qbase, c->H, c->W, batch, stride, rem, ap.nsub, 32 * tps) ||
+            !make_subrow_map(&tml, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, lbase, c->H, c->W, batch, stride, rem, ap.nsub, 32 * tps)) {
+            use5 = false;
+        } else {
+            const uint16_t* tbl = c->sptable + (update ? 0 : SPT_MAX_ELEMS);
+            const assign5_fn fn = pick_assign5(g.TS, update, tps);
+            const long supers = (long)ceil_div(ap.tiles_x, tps) * ap.tiles_y * batch;
+            long grid = (supers + warps5 - 1) / warps5;
+            if (grid > c->num_sms) grid = c->num_sms;
+            cudaEvent_t e0 = nullptr, e1 = nullptr;
+            if (c->kev_on && update) {
+                while ((int)c->kev.size() < c->kev_used + 2) {
+                    cudaEvent_t e;
+                    CK(cudaEventCreate(&e));
+                    c->kev.push_back(e);
+                }
+                e0 = c->kev[c->kev_used++];
+                e1 = c->kev[c->kev_used++];
+                CK(cudaEventRecord(e0, st));
+            }
+            fn<<<(int)grid, 32 * warps5, smem5, st>>>(ap, tmq, tml, qbase, lbase, SL_CINFO(c), SL_CELLS(c), SL_ACC(c), tbl);
+            if (e1) CK(cudaEventRecord(e1, st));
+            c->last_assign_impl = 5;
+        }
+    }
+    if (use5) {
+        // launched above
+    } else if (g.fast) {
+        c->last_assign_impl = 4;
         const uint16_t* tbl = c->sptable + (update ? 0 : SPT_MAX_ELEMS);
         const assign_fn fn = pick_assign(g.TS, stride, update);
         int occ = 1;
@@ -577,6 +695,7 @@ static int run_assign_pass(fslic_ctx* c, int batch, int stride, int rem, int cfg
         fn<<<(int)grid, AS_THREADS, g.smem, st>>>(ap, SL_QUAD(c), SL_LABELS(c), SL_CINFO(c), SL_CELLS(c), SL_ACC(c), tbl);
         if (e1) CK(cudaEventRecord(e1, st));
     } else {
+        c->last_assign_impl = 0;
         const long px = (long)ap.nsub * c->W * batch;
         long grid = (px + 255) / 256;
         if (grid > (long)c->num_sms * 64) grid = (long)c->num_sms * 64;

@@ -110,7 +110,11 @@ __global__ void k_init_clusters(const uint8_t* __restrict__ images, fslic_cluste
     fslic_cluster c;
     c.y = (float)cy;
     c.x = (float)cx;
-    const size_t img = ((size_t)b * H * W + (size_t)cy * W + cx) * 3;
+    // context.cpp:88 evaluates `W * clusters[k].y + clusters[k].x` on float operands -- one fused multiply-add under
+    // the reference's build flags (setup.py:137-149, -mfma) -- and truncates: above 2^24 pixels that is not always
+    // the exact pixel index.  Same arithmetic here (clamped into the image for memory safety only).
+    const int base = min((int)__fmaf_rn((float)W, (float)cy, (float)cx), H * W - 1);
+    const size_t img = ((size_t)b * H * W + (size_t)base) * 3;
     c.r = images[img];
     c.g = images[img + 1];
     c.b = images[img + 2];

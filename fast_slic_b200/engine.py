@@ -176,5 +176,9 @@ class Engine:
         check(self._L.fslic_b200_debug_cca_counters(self._h, out, image))
         return dict(zip(("ncomp", "ncand", "nkept", "sel_mode", "keep_thres", "need_sim", "heap_ops", "kth_area"), list(out)))
 
+    def assign_impl(self):
+        """5: TMA-staged assign kernel, 4: LDG kernel, 0: brute force (last pass of the last iterate)."""
+        return int(self._L.fslic_b200_debug_assign_impl(self._h))
+
     def launches_last_iterate(self):
         return int(self._L.fslic_b200_launches_last_iterate(self._h))

@@ -141,6 +141,11 @@ int fslic_b200_stage_ms(fslic_ctx* ctx, float* out_ms, int count);
 int fslic_b200_get_S(const fslic_ctx* ctx);
 int fslic_b200_launches_last_iterate(const fslic_ctx* ctx);
 
+/* Diagnostics: which assign kernel the last pass of the last iterate() used -- 5: the TMA-staged kernel
+ * (k_assign5; needs W % 8 == 0 and subsample_stride 3), 4: the LDG kernel (k_assign_warp; any shape; forced
+ * by the environment variable FSLIC_ASSIGN=4 at context creation), 0: the brute-force kernel / none yet. */
+int fslic_b200_debug_assign_impl(const fslic_ctx* ctx);
+
 #ifdef __cplusplus
 }
 #endif

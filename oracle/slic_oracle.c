@@ -142,7 +142,11 @@ void orc_initialize_clusters(int H, int W, int K, const uint8_t* image, OrcClust
         acc_k++;
     }
     for (int k = 0; k < K; k++) {
-        int base = W * (int)clusters[k].y + (int)clusters[k].x;
+        /* context.cpp:88 computes `W * clusters[k].y + clusters[k].x` on FLOAT operands; with the reference's own
+         * build flags (setup.py:137-149: -mfma, GCC's default -ffp-contract=fast) that is ONE fused multiply-add,
+         * truncated to int.  Above 2^24 pixels the float result is not the exact pixel index any more (odd indices
+         * round to a neighbour): reproduced here with fmaf(), which is exactly that instruction's arithmetic. */
+        int base = (int)fmaf((float)W, clusters[k].y, clusters[k].x);
         clusters[k].r = image[3 * base];
         clusters[k].g = image[3 * base + 1];
         clusters[k].b = image[3 * base + 2];

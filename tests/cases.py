@@ -63,6 +63,29 @@ EDGE_CASES = [
     ("w31", "syn", 70, 31, 9, {}),
 ]
 
+# shapes aimed at the TMA-staged assign kernel (W % 8 == 0): widths that are / are not multiples of the 32- and
+# 128-column tiles, heights that leave ragged sub-row groups, small S (single-tile super tiles, list overflow),
+# uncovered pixels, warm start is covered separately
+TMA_CASES = [
+    ("tma_97x136_K37", "syn", 97, 136, 37, dict(min_size_factor=0.1)),
+    ("tma_123x200_K60_msf0", "syn", 123, 200, 60, dict(min_size_factor=0.0)),
+    ("tma_250x264_K100", "noise", 250, 264, 100, {}),
+    ("tma_131x128_K50_flat", "flat", 131, 128, 50, dict(min_size_factor=0.5)),
+    ("tma_200x328_blocks_K150", "blocks", 200, 328, 150, dict(min_size_factor=0.0)),
+    ("tma_S8_160x160_K400", "syn", 160, 160, 400, dict(min_size_factor=0.0)),
+    ("tma_S16_256x256_K256", "noise", 256, 256, 256, dict(min_size_factor=0.0)),
+    ("tma_S5_96x104_K350", "syn", 96, 104, 350, dict(min_size_factor=0.0)),
+    ("tma_thin_13x520_K6", "syn", 13, 520, 6, {}),
+    ("tma_thin_500x8_K5", "syn", 500, 8, 5, {}),
+    ("tma_1row_1x256_K9", "syn", 1, 256, 9, {}),
+    ("tma_compact40_300x400_K200", "syn", 300, 400, 200, dict(compactness=40.0)),
+    ("tma_rgb_222x344_K99", "syn", 222, 344, 99, dict(convert_to_lab=False)),
+    ("tma_it1_150x200_K30", "syn", 150, 200, 30, dict(max_iter=1)),
+    ("tma_it2_150x200_K30", "syn", 150, 200, 30, dict(max_iter=2, min_size_factor=0.0)),
+    ("tma_S60_700x1000_K190", "syn", 700, 1000, 190, dict(min_size_factor=0.0)),
+    ("tma_S90_900x1200_K130", "syn", 900, 1200, 130, dict(min_size_factor=0.0)),
+]
+
 BIG_CASES = [
     ("B_1280x720_K1600_msf0", "syn", 720, 1280, 1600, dict(min_size_factor=0.0)),
     ("B_1280x720_K1600_msf.1_s40", "syn", 720, 1280, 1600, dict(min_size_factor=0.1, sigma=40.0)),

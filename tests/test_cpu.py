@@ -73,6 +73,23 @@ def test_oracle_matches_compiled_reference_edge(port, ref, case):
     assert (o1 == o2).all() and c1.tobytes() == c2.tobytes()
 
 
+def test_oracle_initialize_above_2p24_pixels(port):
+    """context.cpp:88 indexes the image with a FLOAT expression (one fused multiply-add under the reference's build
+    flags); above 2^24 pixels it lands on a neighbouring pixel for some centres.  Known answer = SHA-256 of the
+    compiled reference's Cluster bytes for this seeded 4100x4200 image (found by the round-2 GPU run: the restatement
+    used exact integer indexing until then)."""
+    img = make_image("tiled", 4100, 4200, seed=11, sigma=20.0)
+    cl = port.initialize(img, 3000)
+    assert hashlib.sha256(cl.tobytes()).hexdigest() == "f344f4422d2aae58b78e3c8f096b7bb1969c8289666fb817d5a5e59a07c71b3b"
+    exact = np.array([img[int(c["y"]), int(c["x"])] for c in cl], np.float32)
+    assert (np.stack([cl["r"], cl["g"], cl["b"]], 1) != exact).any(), "the case must exercise the inexact index"
+
+
+def test_oracle_initialize_above_2p24_pixels_live(port, ref):
+    img = make_image("tiled", 4100, 4200, seed=11, sigma=20.0)
+    assert port.initialize(img, 3000).tobytes() == ref.initialize(img, 3000).tobytes()
+
+
 @pytest.mark.parametrize("seed", range(10))
 def test_oracle_matches_compiled_reference_random_configs(port, ref, seed):
     """Seeded random shapes / K / parameters: the restatement against the compiled reference, all stages."""

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from cases import BIG_CASES, EDGE_CASES, PIPELINE_CASES, make_image, split_kwargs
+from cases import BIG_CASES, EDGE_CASES, PIPELINE_CASES, TMA_CASES, make_image, split_kwargs
 
 pytestmark = pytest.mark.gpu
 
@@ -71,6 +71,33 @@ def test_pipeline_parity_edge(checker, case):
     sigma, args = split_kwargs(kw)
     img = make_image(kind, H, W, seed=5, sigma=sigma)
     _compare(name, _run_cuda(img, K, args), _run_oracle(checker, img, K, args))
+
+
+@pytest.mark.parametrize("case", TMA_CASES, ids=[c[0] for c in TMA_CASES])
+def test_pipeline_parity_tma_kernel(checker, case):
+    name, kind, H, W, K, kw = case
+    sigma, args = split_kwargs(kw)
+    img = make_image(kind, H, W, seed=23, sigma=sigma)
+    _compare(name, _run_cuda(img, K, args), _run_oracle(checker, img, K, args))
+    eng = _engine(H, W, K)
+    assert eng.S > 110 or eng.assign_impl() == 5, "the TMA-staged kernel did not run (impl %d)" % eng.assign_impl()
+
+
+@pytest.mark.parametrize("case", [PIPELINE_CASES[0], PIPELINE_CASES[3], TMA_CASES[1], TMA_CASES[5], BIG_CASES[0]],
+                         ids=lambda c: c[0])
+def test_pipeline_parity_ldg_kernel_forced(checker, monkeypatch, case):
+    """FSLIC_ASSIGN=4 keeps the round-1 LDG kernel selectable (it is the path of every W % 8 != 0 image)."""
+    from fast_slic_b200 import clear_engine_cache
+    monkeypatch.setenv("FSLIC_ASSIGN", "4")
+    clear_engine_cache()
+    try:
+        name, kind, H, W, K, kw = case
+        sigma, args = split_kwargs(kw)
+        img = make_image(kind, H, W, seed=29, sigma=sigma)
+        _compare(name, _run_cuda(img, K, args), _run_oracle(checker, img, K, args))
+        assert _engine(H, W, K).assign_impl() in (0, 4)
+    finally:
+        clear_engine_cache()
 
 
 def test_rejects_what_the_reference_cannot_do():
