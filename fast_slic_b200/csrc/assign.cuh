@@ -177,6 +177,12 @@ struct AssignParams {
     int tiles_x, tiles_y, ntiles;  // warp tiles (32 columns x R sub-rows) per image
     int tps;           // warp tiles per super tile: AS_T, or 1 when the launch is too small to fill the GPU otherwise
     float coef;        // generic path only
+    // k_assign5 only: everything warp uniform that the host can precompute lives in the constant bank, so the kernel
+    // neither keeps it in registers nor re-derives it (the compiler rematerialised the divisions per super tile)
+    int stx, per_img, total;        // super tiles per tile row / per image / in all
+    int wstride, db, dty, dsx;      // a warp's step through the super tiles, decomposed into (image, tile row, column) carries
+    uint32_t tbl_bytes;             // patch size in shared memory, padded to 128 bytes
+    uint32_t cinfo_img_bytes, cells_img_bytes, acc_img_bytes;  // per-image pitches of cinfo / cell_start / acc
 };
 
 #define AS_WARPS 16

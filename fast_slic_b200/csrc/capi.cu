@@ -22,7 +22,7 @@ typedef void (*assign_fn)(AssignParams, const uint32_t*, uint16_t*, const CInfo*
                           const uint16_t*);
 static assign_fn pick_assign(int TS, int stride, bool update);
 
-typedef void (*assign5_fn)(AssignParams, const CUtensorMap, const CUtensorMap, const uint32_t*, uint16_t*, const CInfo*,
+typedef void (*assign5_fn)(const AssignParams, const CUtensorMap, const CUtensorMap, const uint32_t*, uint16_t*, const CInfo*,
                            const int*, unsigned long long*, const uint16_t*);
 static assign5_fn pick_assign5(int TS, bool update, int tps);
 
@@ -617,13 +617,13 @@ static int run_assign_pass(fslic_ctx* c, int batch, int stride, int rem, int cfg
     // labels), the sub-row pitch is an immediate of its patch loads (stride 3 with the update, 1 without), and its
     // per-warp shared blocks must fit beside the patch.  Everything else takes the LDG kernel below.
     bool use5 = g.fast && c->assign_impl == 5 && (c->W % 8) == 0 && g.TS <= 256 && (update ? stride == 3 : stride == 1) &&
-                tensor_map_encoder() != nullptr;
+                (long)ceil_div(c->W, 32) * ap.tiles_y * batch < (1L << 30) && tensor_map_encoder() != nullptr;
     int warps5 = 0;
     size_t smem5 = 0;
     if (use5) {
         const size_t tblb = align_up((size_t)g.tbl_elems * 2, 128);
         for (int w : {32, 16, 8}) {
-            smem5 = tblb + (size_t)w * A5_WBLK + (size_t)w * 8;
+            smem5 = tblb + (size_t)w * A5_WBLK;
             if (smem5 <= (size_t)(c->max_smem_optin - 1024)) {
                 warps5 = w;
                 break;
@@ -650,6 +650,18 @@ static int run_assign_pass(fslic_ctx* c, int batch, int stride, int rem, int cfg
             const long supers = (long)ceil_div(ap.tiles_x, tps) * ap.tiles_y * batch;
             long grid = (supers + warps5 - 1) / warps5;
             if (grid > c->num_sms) grid = c->num_sms;
+            // the warp-uniform walk constants (constant bank; see the note on code generation in assign5.cuh)
+            ap.stx = ceil_div(ap.tiles_x, tps);
+            ap.per_img = ap.stx * ap.tiles_y;
+            ap.total = (int)supers;
+            ap.wstride = (int)grid * warps5;
+            ap.db = ap.wstride / ap.per_img;
+            ap.dty = (ap.wstride % ap.per_img) / ap.stx;
+            ap.dsx = (ap.wstride % ap.per_img) % ap.stx;
+            ap.tbl_bytes = (uint32_t)align_up((size_t)g.tbl_elems * 2, 128);
+            ap.cinfo_img_bytes = (uint32_t)c->K * (uint32_t)sizeof(CInfo);
+            ap.cells_img_bytes = (uint32_t)(c->ncell + 1) * 4u;
+            ap.acc_img_bytes = (uint32_t)c->K * 32u;
             cudaEvent_t e0 = nullptr, e1 = nullptr;
             if (c->kev_on && update) {
                 while ((int)c->kev.size() < c->kev_used + 2) {
