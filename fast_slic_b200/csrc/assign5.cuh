@@ -389,6 +389,8 @@ __global__ void __launch_bounds__(32 * A5_MAXWARPS, 1)
                 a5_sts128<A5_OFF_SCR + 16>(fa, __byte_perm(lo01, lo23, 0x7632), __byte_perm(hi01, hi23, 0x5410), 0u, 0u);
                 __syncwarp();
                 const uint32_t fb = wb + tig * 32 + g * 4;  // feature g of pixel lanes tig, tig + 4 (+ 8 s4)
+                const uint32_t flo = tig == 1 ? (uint32_t)tj0 : 0u, fhi = tig == 0 ? (uint32_t)wi0 : 0u;
+                const uint32_t fmul = tig == 0 ? (uint32_t)stride : 1u;
                 const int n16 = (n_t + 15) >> 4;
                 for (int nt = 0; nt < n16; nt++) {
                     int d[4] = {0, 0, 0, 0};
@@ -413,7 +415,11 @@ __global__ void __launch_bounds__(32 * A5_MAXWARPS, 1)
                         A5_MMA1(0) A5_MMA1(1) A5_MMA1(2) A5_MMA1(3)
 #undef A5_MMA1
                     }
-                    // sums are scaled by 128 (the one-hot byte is 0x80)
+                    // sums are scaled by 128 (the one-hot byte is 0x80).  Packed accumulator word `tig` of a candidate:
+                    //   tig 0: n | sum_y << 32   = v0            | (v1 * stride + n * wi0) << 32     (v0 = n, v1 = sum of row indices)
+                    //   tig 1: sum_x | sum_L<<32 = v0 + n * tj0  | v1 << 32                          (v0 = sum of lane indices)
+                    //   tig 2: sum_a | sum_b<<32 = v0            | v1 << 32
+                    // i.e. lo = v0 + n * flo, hi = v1 * fmul + n * fhi with three per-lane constants: no branches.
 #pragma unroll
                     for (int hh = 0; hh < 2; hh++) {
                         if (hh == 1 && !two) break;
@@ -421,15 +427,9 @@ __global__ void __launch_bounds__(32 * A5_MAXWARPS, 1)
                         const uint32_t v0 = (uint32_t)d[2 * hh] >> 7, v1 = (uint32_t)d[2 * hh + 1] >> 7;
                         const uint32_t cnt = __shfl_sync(FSLIC_FULL, v0, lane & ~3u);  // feature 0 lives in the tig = 0 lane
                         if (c < n_t && tig < 3 && cnt != 0) {
-                            unsigned long long word;
-                            if (tig == 0)
-                                word = (unsigned long long)cnt |
-                                       ((unsigned long long)(cnt * (uint32_t)wi0 + (uint32_t)stride * v1) << 32);
-                            else if (tig == 1)
-                                word = (unsigned long long)(cnt * (uint32_t)tj0 + v0) | ((unsigned long long)v1 << 32);
-                            else
-                                word = (unsigned long long)v0 | ((unsigned long long)v1 << 32);
-                            atomicAdd(&ac[a5_lds16<A5_OFF_TK>(tk + (uint32_t)c * 2) * 4 + tig], word);
+                            const uint32_t lo = v0 + cnt * flo, hi = v1 * fmul + cnt * fhi;
+                            atomicAdd(&ac[a5_lds16<A5_OFF_TK>(tk + (uint32_t)c * 2) * 4 + tig],
+                                      (unsigned long long)lo | ((unsigned long long)hi << 32));
                         }
                     }
                 }

@@ -294,6 +294,7 @@ static int create_impl(int device, int H, int W, int K, int max_batch, bool cca_
     CKC(cudaFuncSetAttribute(k_cca_select, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin - 4 * 1024));
     CKC(cudaFuncSetAttribute(k_debug_heap_select, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin - 4 * 1024));
     CKC(cudaFuncSetAttribute(k_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+    CKC(cudaFuncSetAttribute(k_rgb_to_lab16, cudaFuncAttributeMaxDynamicSharedMemorySize, LAB16_SMEM));
     *out = c;
     return FSLIC_OK;
 }
@@ -332,7 +333,15 @@ static int launch_lab(fslic_ctx* c, const uint8_t* d_images, uint32_t* quad, int
     const long cap = (long)c->num_sms * 16;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    k_rgb_to_quad<<<(int)blocks, 256, 0, st>>>(d_images, quad, npix, c->d_gamma, c->d_labtbl, c->lc, convert_to_lab);
+    if (convert_to_lab && ((reinterpret_cast<uintptr_t>(d_images) | reinterpret_cast<uintptr_t>(quad)) & 15) == 0 && npix >= 4096) {
+        // persistent CTAs: the 48 KB of tables are filled once per CTA
+        long nb = (npix / 16 + 255) / 256;
+        if (nb > (long)c->num_sms * 4) nb = (long)c->num_sms * 4;
+        if (nb < 1) nb = 1;
+        k_rgb_to_lab16<<<(int)nb, 256, LAB16_SMEM, st>>>(d_images, quad, npix, c->d_gamma, c->d_labtbl, c->lc);
+    } else {
+        k_rgb_to_quad<<<(int)blocks, 256, 0, st>>>(d_images, quad, npix, c->d_gamma, c->d_labtbl, c->lc, convert_to_lab);
+    }
     CK(cudaGetLastError());
     return FSLIC_OK;
 }
@@ -648,6 +657,23 @@ static int run_assign_pass(fslic_ctx* c, int batch, int stride, int rem, int cfg
             const uint16_t* tbl = c->sptable + (update ? 0 : SPT_MAX_ELEMS);
             const assign5_fn fn = pick_assign5(g.TS, update, tps);
             const long supers = (long)ceil_div(ap.tiles_x, tps) * ap.tiles_y * batch;
+            // Super tiles are handed out statically, so a launch lasts ceil(supers / warps) rounds: with ~4 rounds (720p x 32)
+            // a full grid of 32-warp CTAs idles a fifth of the time in the last round.  The kernel is issue bound and
+            // saturates an SM with fewer warps, so take the warp count (>= 3/4 of the maximum) that wastes the least.
+            if (supers > (long)c->num_sms * warps5) {
+                int best_w = warps5;
+                double best_cost = 1e30;
+                for (int w = warps5; w >= (warps5 * 3) / 4; w--) {
+                    const long workers = (long)c->num_sms * w;
+                    const double cost = (double)((supers + workers - 1) / workers) * w;  // rounds x warps sharing an SM
+                    if (cost < best_cost * 0.995) {
+                        best_cost = cost;
+                        best_w = w;
+                    }
+                }
+                warps5 = best_w;
+                smem5 = align_up((size_t)g.tbl_elems * 2, 128) + (size_t)warps5 * A5_WBLK;
+            }
             long grid = (supers + warps5 - 1) / warps5;
             if (grid > c->num_sms) grid = c->num_sms;
             // the warp-uniform walk constants (constant bank; see the note on code generation in assign5.cuh)

@@ -73,6 +73,64 @@ __global__ void __launch_bounds__(256) k_rgb_to_quad(const uint8_t* __restrict__
     }
 }
 
+// Round-2 form of the Lab branch.  ncu on the kernel above (720p x 32): the LSU pipe sits at 86 % of its wavefront
+// peak -- six u16 table gathers per pixel with 2.8-way bank conflicts on average -- and the ALU pipe at 65 %.
+// Here the 256-entry gamma table is replicated 32 times in shared memory, word (v * 32 + lane): every lane reads its own
+// bank, so the three gamma gathers of a pixel are conflict free (the 8193-entry Lab table cannot be replicated and
+// keeps its conflicts); a thread converts 16 consecutive pixels per step: 3 x LDG.128 in, 4 x STG.128 out.
+// Same integer arithmetic, same tables (cielab.h:308-325).  Needs 16-byte aligned bases; pixels beyond the last full
+// group of 16 are converted one by one by the last thread.
+#define LAB16_SMEM (256 * 32 * 4 + 8200 * 2)
+__device__ __forceinline__ uint32_t lab_one_pixel(int sr, int sg, int sb, const uint16_t* s_lab, const LabConsts& lc) {
+    const int xr = (lc.Cb[0] * sr + lc.Cb[1] * sg + lc.Cb[2] * sb) >> 16;
+    const int yr = (lc.Cb[3] * sr + lc.Cb[4] * sg + lc.Cb[5] * sb) >> 16;
+    const int zr = (lc.Cb[6] * sr + lc.Cb[7] * sg + lc.Cb[8] * sb) >> 16;
+    const int fx = s_lab[xr], fy = s_lab[yr], fz = s_lab[zr];
+    const int ciel = 116 * fy - (16 << 13);
+    const int ciea = 500 * (fx - fy) + (128 << 13);
+    const int cieb = 200 * (fy - fz) + (128 << 13);
+    // unsigned shift, unsigned subtract, then clamp as int -- exactly cielab.h:322-324
+    const int l = min(max((int)((unsigned)ciel >> 12), 0), 255);
+    const int a = min(max((int)(((unsigned)ciea >> 12) - 128u), 0), 255);
+    const int b = min(max((int)(((unsigned)cieb >> 12) - 128u), 0), 255);
+    return (uint32_t)l | ((uint32_t)a << 8) | ((uint32_t)b << 16);
+}
+
+__global__ void __launch_bounds__(256) k_rgb_to_lab16(const uint8_t* __restrict__ rgb, uint32_t* __restrict__ quad, long npix,
+                                                       const uint16_t* __restrict__ g_gamma,
+                                                       const uint16_t* __restrict__ g_labtbl, LabConsts lc) {
+    extern __shared__ __align__(16) unsigned char lab_smem[];
+    uint32_t* s_gam = reinterpret_cast<uint32_t*>(lab_smem);                       // [256][32]
+    uint16_t* s_lab = reinterpret_cast<uint16_t*>(lab_smem + 256 * 32 * 4);        // [8193]
+    for (int t = threadIdx.x; t < 256 * 32; t += blockDim.x) s_gam[t] = g_gamma[t >> 5];
+    for (int t = threadIdx.x; t < 8193; t += blockDim.x) s_lab[t] = g_labtbl[t];
+    __syncthreads();
+    const uint32_t* gam = s_gam + (threadIdx.x & 31);  // this lane's copy: gam[v * 32]
+    const long ngroups = npix >> 4;
+    const uint4* src = reinterpret_cast<const uint4*>(rgb);
+    uint4* dst = reinterpret_cast<uint4*>(quad);
+    for (long gi = (long)blockIdx.x * blockDim.x + threadIdx.x; gi < ngroups; gi += (long)gridDim.x * blockDim.x) {
+        const uint4 w0 = __ldg(src + 3 * gi), w1 = __ldg(src + 3 * gi + 1), w2 = __ldg(src + 3 * gi + 2);
+        const uint32_t w[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
+        uint32_t out[16];
+#pragma unroll
+        for (int t = 0; t < 16; t++) {
+            // byte 3t + c of the 48-byte group
+            const int o0 = 3 * t, o1 = 3 * t + 1, o2 = 3 * t + 2;
+            const uint32_t R = (w[o0 >> 2] >> (8 * (o0 & 3))) & 0xffu;
+            const uint32_t G = (w[o1 >> 2] >> (8 * (o1 & 3))) & 0xffu;
+            const uint32_t B = (w[o2 >> 2] >> (8 * (o2 & 3))) & 0xffu;
+            out[t] = lab_one_pixel((int)gam[R * 32], (int)gam[G * 32], (int)gam[B * 32], s_lab, lc);
+        }
+#pragma unroll
+        for (int v = 0; v < 4; v++) dst[4 * gi + v] = make_uint4(out[4 * v], out[4 * v + 1], out[4 * v + 2], out[4 * v + 3]);
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == blockDim.x - 1) {
+        for (long p = ngroups << 4; p < npix; p++)
+            quad[p] = lab_one_pixel((int)gam[rgb[3 * p] * 32], (int)gam[rgb[3 * p + 1] * 32], (int)gam[rgb[3 * p + 2] * 32], s_lab, lc);
+    }
+}
+
 // Replaces BaseContext::initialize_clusters (/root/reference/src/context.cpp:43-97).
 // One thread per (image, cluster): walks the row bands to find the band / column its index falls
 // in (O(sqrt K)), then samples the raw RGB at the centre.  Runs once per model, not per iterate.
