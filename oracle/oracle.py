@@ -113,6 +113,34 @@ class Port:
         self.lib.stl_partial_sort_by_area(_p(comps, _i32p), C.c_long(len(area)), C.c_long(middle), _p(area, _i32p))
         return np.sort(comps[:middle])
 
+    # ---- consumers of the label map (fast-slic.cpp:16-168) ----
+    def get_connectivity(self, labels, K):
+        labels = np.ascontiguousarray(labels, np.uint16)
+        H, W = labels.shape
+        counts = np.zeros(K, np.int32)
+        nb = np.zeros((K, 12), np.uint32)
+        self.lib.orc_get_connectivity(H, W, K, _p(labels, _u16p), _p(counts, _i32p), nb.ctypes.data_as(C.c_void_p))
+        return [nb[k, :counts[k]].tolist() for k in range(K)]
+
+
+    def get_mask_density(self, clusters, labels, mask):
+        labels = np.ascontiguousarray(labels, np.uint16)
+        mask = np.ascontiguousarray(mask, np.uint8)
+        H, W = labels.shape
+        K = len(clusters)
+        dens = np.zeros(K, np.uint8)
+        self.lib.orc_get_mask_density(H, W, K, clusters.ctypes.data_as(C.c_void_p), _p(labels, _u16p), _p(mask, _u8p),
+                                      _p(dens, _u8p))
+        return dens
+
+    def density_to_mask(self, K, labels, densities):
+        labels = np.ascontiguousarray(labels, np.uint16)
+        densities = np.ascontiguousarray(densities, np.uint8)
+        H, W = labels.shape
+        out = np.zeros((H, W), np.uint8)
+        self.lib.orc_cluster_density_to_mask(H, W, K, _p(labels, _u16p), _p(densities, _u8p), _p(out, _u8p))
+        return out
+
 
 class Ref:
     """The unmodified reference (standard or x64/avx2 arch), OpenMP threads = num_threads (-1: all)."""
@@ -150,4 +178,34 @@ class Ref:
         out = np.ascontiguousarray(labels.astype(np.uint16))
         H, W = out.shape
         self.lib.ref_enforce_connectivity(_p(out, _u16p), H, W, K, thres, num_threads)
+        return out
+
+    # ---- consumers of the label map: the reference's own fast-slic.o behind oracle/ref_shim.cpp ----
+    def get_connectivity(self, labels, K):
+        labels = np.ascontiguousarray(labels, np.uint16)
+        H, W = labels.shape
+        counts = np.zeros(K, np.int32)
+        nb = np.zeros((K, 12), np.uint32)
+        self.lib.ref_get_connectivity(H, W, K, _p(labels, _u16p), _p(counts, _i32p), nb.ctypes.data_as(C.c_void_p))
+        return [nb[k, :counts[k]].tolist() for k in range(K)]
+
+
+    def get_mask_density(self, clusters, labels, mask):
+        labels = np.ascontiguousarray(labels, np.uint16)
+        mask = np.ascontiguousarray(mask, np.uint8)
+        H, W = labels.shape
+        K = len(clusters)
+        dens = np.zeros(K, np.uint8)
+        self.lib.ref_get_mask_density(H, W, K, clusters.ctypes.data_as(C.c_void_p), _p(labels, _u16p), _p(mask, _u8p),
+                                      _p(dens, _u8p))
+        return dens
+
+    def density_to_mask(self, K, labels, densities):
+        labels = np.ascontiguousarray(labels, np.uint16)
+        densities = np.ascontiguousarray(densities, np.uint8)
+        H, W = labels.shape
+        out = np.zeros((H, W), np.uint8)
+        clusters = np.zeros(K, CLUSTER_DTYPE)
+        self.lib.ref_cluster_density_to_mask(H, W, K, clusters.ctypes.data_as(C.c_void_p), _p(labels, _u16p),
+                                             _p(densities, _u8p), _p(out, _u8p))
         return out

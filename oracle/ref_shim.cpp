@@ -14,6 +14,7 @@
 #include "cca.h"
 #include "parallel.h"
 #include "arch/x64/avx2.h"
+#include "fast-slic.h"
 
 namespace {
 struct ProbeAvx2 : public fslic::Context_X64_AVX2 {
@@ -91,6 +92,26 @@ void ref_enforce_connectivity(uint16_t* labels, int H, int W, int K, int min_thr
     fsparallel::Scope scope(num_threads);
     cca::ConnectivityEnforcer ce(labels, H, W, K, min_threshold);
     ce.execute(labels);
+}
+
+// fast-slic.cpp:16-78 through the door cfast_slic.pyx:262-270 uses.  counts[K], neighbors[K * 12] (max_conn = 12).
+void ref_get_connectivity(int H, int W, int K, const uint16_t* assignment, int32_t* counts, uint32_t* neighbors) {
+    Connectivity* conn = fast_slic_get_connectivity(H, W, K, assignment);
+    for (int k = 0; k < K; k++) {
+        counts[k] = conn->num_neighbors[k];
+        for (int t = 0; t < conn->num_neighbors[k] && t < 12; t++) neighbors[k * 12 + t] = conn->neighbors[k][t];
+    }
+    fast_slic_free_connectivity(conn);
+}
+
+// fast-slic.cpp:141-168 (cfast_slic.pyx:283-320)
+void ref_get_mask_density(int H, int W, int K, const Cluster* clusters, const uint16_t* assignment, const uint8_t* mask,
+                          uint8_t* densities) {
+    fast_slic_get_mask_density(H, W, K, clusters, assignment, mask, densities);
+}
+void ref_cluster_density_to_mask(int H, int W, int K, const Cluster* clusters, const uint16_t* assignment,
+                                 const uint8_t* densities, uint8_t* result) {
+    fast_slic_cluster_density_to_mask(H, W, K, clusters, assignment, densities, result);
 }
 
 }  // extern "C"

@@ -488,3 +488,59 @@ void orc_update(int H, int W, int K, OrcCluster* clusters, const uint8_t* quad, 
                 int rem) {
     update_pass(H, W, K, clusters, quad, assignment, stride, rem);
 }
+
+/* ------------------------------------------------------------------ */
+/* consumers of the label map: src/fast-slic.cpp:16-168                */
+/* ------------------------------------------------------------------ */
+#define ORC_MAX_CONN 12 /* fast-slic.cpp:17 */
+
+/* fast_slic_get_connectivity, fast-slic.cpp:16-78.  The reference's K-word bit set only short-cuts the membership
+ * test (a pair is linked <=> it is in both lists), so it is restated as the plain list search it guards.
+ * counts[K], neighbors[K * 12]. */
+void orc_get_connectivity(int H, int W, int K, const uint16_t* assignment, int32_t* counts, uint32_t* neighbors) {
+    for (int k = 0; k < K; k++) counts[k] = 0;
+    for (int i = 0; i < H - 1; i++) {
+        for (int j = 0; j < W - 1; j++) {
+            long base = (long)W * i + j;
+            uint32_t source = assignment[base];
+            if (source >= (uint32_t)K) continue;            /* :35 */
+            int ns = counts[source];                        /* cached for the three probes, written back at :71 */
+            const long probe[3] = {base + 1, base + W, base + W + 1}; /* :69-71 */
+            for (int t = 0; t < 3; t++) {
+                uint32_t target = assignment[probe[t]];
+                if (target >= (uint32_t)K || source == target) continue;          /* :41 */
+                int nt = counts[target];
+                if (ns >= ORC_MAX_CONN || nt >= ORC_MAX_CONN) continue;           /* :43 */
+                int exists = 0;
+                for (int u = 0; u < ns && !exists; u++) exists = neighbors[source * ORC_MAX_CONN + u] == target; /* :47-52 */
+                for (int u = 0; u < nt && !exists; u++) exists = neighbors[target * ORC_MAX_CONN + u] == source; /* :54-59 */
+                if (exists) continue;
+                neighbors[target * ORC_MAX_CONN + counts[target]++] = source;      /* :62 */
+                neighbors[source * ORC_MAX_CONN + ns++] = target;                  /* :63 */
+            }
+            counts[source] = ns;                                                   /* :72 */
+        }
+    }
+}
+
+/* fast_slic_knn_connectivity (fast-slic.cpp:80-130) is NOT restated: it files every cluster under the cell index
+ * (y / S) * nw + (x / S) evaluated in FLOAT (:88) -- 5.95 * 8 + 7.95 = 55 in a 6 x 8 grid -- so any centre in the lower
+ * part of the last cell row indexes past the end of s_cells (heap overflow; the compiled reference segfaults on a plain
+ * 120 x 160 / K = 48 seeding).  There is no defined behaviour to be identical to. */
+
+/* fast_slic_get_mask_density / fast_slic_cluster_density_to_mask, fast-slic.cpp:141-168 */
+void orc_get_mask_density(int H, int W, int K, const OrcCluster* clusters, const uint16_t* assignment, const uint8_t* mask,
+                          uint8_t* densities) {
+    int* sum = (int*)calloc((size_t)K, sizeof(int));
+    for (long p = 0; p < (long)H * W; p++)
+        if (assignment[p] < (uint16_t)K) sum[assignment[p]] += mask[p];
+    for (int k = 0; k < K; k++) {
+        unsigned den = clusters[k].num_members > 1u ? clusters[k].num_members : 1u;
+        unsigned v = (unsigned)sum[k] / den;
+        densities[k] = (uint8_t)(v < 255u ? v : 255u);
+    }
+    free(sum);
+}
+void orc_cluster_density_to_mask(int H, int W, int K, const uint16_t* assignment, const uint8_t* densities, uint8_t* result) {
+    for (long p = 0; p < (long)H * W; p++) result[p] = assignment[p] < (uint16_t)K ? densities[assignment[p]] : 0;
+}

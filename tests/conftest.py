@@ -60,6 +60,15 @@ class Checker:
         return self._impl.iterate(image, clusters, max_iter, compactness, min_size_factor, stride, convert_to_lab,
                                   stages=stages)
 
+    def get_connectivity(self, labels, K):
+        return self._impl.get_connectivity(labels, K)
+
+    def get_mask_density(self, clusters, labels, mask):
+        return self._impl.get_mask_density(clusters, labels, mask)
+
+    def density_to_mask(self, K, labels, densities):
+        return self._impl.density_to_mask(K, labels, densities)
+
     def enforce_connectivity(self, labels, K, thres):
         if self.kind == "reference":
             return self._impl.enforce_connectivity(labels, K, thres, num_threads=self._threads)

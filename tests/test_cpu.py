@@ -90,6 +90,29 @@ def test_oracle_initialize_above_2p24_pixels_live(port, ref):
     assert port.initialize(img, 3000).tobytes() == ref.initialize(img, 3000).tobytes()
 
 
+@pytest.mark.parametrize("H,W,K,kind,msf", [(120, 160, 48, "syn", 0.25), (97, 131, 37, "noise", 0.0), (200, 300, 150, "blocks", 0.0),
+                                            (64, 64, 1500, "noise", 0.0), (180, 240, 70, "syn", 0.1)])
+def test_oracle_graph_and_density_match_compiled_reference(port, ref, H, W, K, kind, msf):
+    """fast-slic.cpp:16-78, 141-168 (adjacency graph with its 12-neighbour cap, mask density, density broadcast):
+    restatement == compiled reference.  (knn_connectivity, :80-130, overflows its cell vector -- see slic_oracle.c.)"""
+    img = make_image(kind, H, W, seed=17)
+    cl = ref.initialize(img, K)
+    lab = ref.iterate(img, cl, 10, 10.0, msf, 3, True, num_threads=2)
+    assert port.get_connectivity(lab, K) == ref.get_connectivity(lab, K)
+    # saturated nodes (more than 12 distinct neighbours).  Labels >= K are left out: the reference reads
+    # num_neighbors[source] before its range check (fast-slic.cpp:34-35), out of bounds for the 0xFFFF sentinel
+    raw = (make_image("noise", H, W, seed=3)[..., 0].astype(np.uint16) % min(K, 40)).astype(np.uint16)
+    assert port.get_connectivity(raw, K) == ref.get_connectivity(raw, K)
+    mask = make_image("syn", H, W, seed=5)[..., 1]
+    d1, d2 = port.get_mask_density(cl, lab, mask), ref.get_mask_density(cl, lab, mask)
+    assert (d1 == d2).all()
+    assert (port.density_to_mask(K, lab, d1) == ref.density_to_mask(K, lab, d1)).all()
+    big = raw.copy()
+    big[::7, ::5] = 0xFFFF
+    assert (port.density_to_mask(K, big, d1) == ref.density_to_mask(K, big, d1)).all()
+    assert (port.get_mask_density(cl, big, mask) == ref.get_mask_density(cl, big, mask)).all()
+
+
 @pytest.mark.parametrize("seed", range(10))
 def test_oracle_matches_compiled_reference_random_configs(port, ref, seed):
     """Seeded random shapes / K / parameters: the restatement against the compiled reference, all stages."""
