@@ -17,10 +17,12 @@ EXPORTED_SYMBOLS = (
     "fslic_b200_rgb_to_quad", "fslic_b200_debug_heap_select", "fslic_b200_stage_ms", "fslic_b200_get_S",
     "fslic_b200_launches_last_iterate", "fslic_b200_assign_kernel_time", "fslic_b200_debug_cca_counters",
     "fslic_b200_iterate_host_async", "fslic_b200_wait", "fslic_b200_create_cca",
-    "fslic_b200_debug_assign_impl",
+    "fslic_b200_debug_assign_impl", "fslic_b200_connectivity_scratch_bytes", "fslic_b200_get_connectivity",
+    "fslic_b200_get_mask_density", "fslic_b200_cluster_density_to_mask", "fslic_b200_cca_stage_ms",
 )
 
 STAGE_NAMES = ("cielab_conversion", "assign", "update", "full_assign", "enforce_connectivity", "iterate")
+CCA_STAGE_NAMES = ("build_disjoint_set", "flatten", "threshold_by_area", "sort", "substitute", "output")  # cca.cpp:194-263
 
 
 class Params(C.Structure):
@@ -69,9 +71,15 @@ def lib():
     L.fslic_b200_rgb_to_quad.argtypes = [vp, vp, vp, i32, i32, vp]
     L.fslic_b200_debug_heap_select.argtypes = [vp, vp, i32, i32, vp, vp]
     L.fslic_b200_stage_ms.argtypes = [vp, C.POINTER(C.c_float), i32]
+    L.fslic_b200_cca_stage_ms.argtypes = [vp, C.POINTER(C.c_float), i32]
     L.fslic_b200_get_S.argtypes = [vp]
     L.fslic_b200_launches_last_iterate.argtypes = [vp]
     L.fslic_b200_debug_assign_impl.argtypes = [vp]
+    L.fslic_b200_connectivity_scratch_bytes.argtypes = [i32]
+    L.fslic_b200_connectivity_scratch_bytes.restype = C.c_size_t
+    L.fslic_b200_get_connectivity.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, C.c_size_t, vp]
+    L.fslic_b200_get_mask_density.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
+    L.fslic_b200_cluster_density_to_mask.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp]
     L.fslic_b200_assign_kernel_time.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
     L.fslic_b200_debug_cca_counters.argtypes = [vp, C.POINTER(C.c_int32), i32]
     assert L.fslic_b200_sizeof_cluster() == 32

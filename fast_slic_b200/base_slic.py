@@ -215,14 +215,117 @@ class SlicModel(object):
         with _locked(lambda: get_engine(H, W, self._num_components, 1, self.device)) as eng:
             labels = eng.iterate_host(image[None], clusters, params)
             ms = eng.stage_ms()
+            cca = eng.cca_stage_ms()
         self._clusters = clusters[0]
-        self.last_timing_report = json.dumps({
-            "name": "iterate", "duration": int(ms["iterate"] * 1000),
-            "children": [{"name": n, "duration": int(ms[n] * 1000), "children": []}
-                         for n in ("cielab_conversion", "assign", "update", "full_assign", "enforce_connectivity")],
-        })
+
+        def node(name, ms_value, children=()):
+            return {"name": name, "duration": int(ms_value * 1000), "children": list(children)}
+
+        # same tree as fstimer builds (context.cpp:112-192, cca.cpp:194-263); `update` is fused into `assign` here
+        self.last_timing_report = json.dumps(node("iterate", ms["iterate"], [
+            node("cielab_conversion", ms["cielab_conversion"]), node("assign", ms["assign"]), node("update", ms["update"]),
+            node("full_assign", ms["full_assign"]),
+            node("enforce_connectivity", ms["enforce_connectivity"],
+                 [node("cca", ms["enforce_connectivity"], [node(n, cca[n]) for n in _lib.CCA_STAGE_NAMES])]),
+        ]))
         self.last_recorder_report = b'{"snapshots":[]}'
         return labels[0]
+
+
+class NodeConnectivity(object):
+    """== cfast_slic.NodeConnectivity (cfast_slic.pyx:322-345): `tolist()` -> list of neighbour lists."""
+
+    def __init__(self, counts, neighbors):
+        self._counts, self._neighbors = counts, neighbors
+
+    def tolist(self):
+        return [self._neighbors[k, :self._counts[k]].tolist() for k in range(len(self._counts))]
+
+
+def _check_assignments(assignments):
+    if not isinstance(assignments, np.ndarray) or assignments.dtype != np.int16 or assignments.ndim != 2 \
+            or not assignments.flags["C_CONTIGUOUS"]:
+        raise ValueError("assignments must be a C-contiguous int16[H, W] array")
+    return assignments
+
+
+def _graph_get_connectivity(self, assignments):
+    """cfast_slic.pyx:262-270 -> fast_slic_get_connectivity (fast-slic.cpp:16-78) on the GPU."""
+    assignments = _check_assignments(assignments)
+    require_cuda()
+    H, W = assignments.shape
+    K = self.num_components
+    dev = torch.device("cuda", self.device)
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        lab = torch.from_numpy(assignments).to(dev)
+        counts = torch.empty(K, dtype=torch.int32, device=dev)
+        nb = torch.empty((K, 12), dtype=torch.int32, device=dev)
+        nbytes = int(L.fslic_b200_connectivity_scratch_bytes(K))
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _lib.check(L.fslic_b200_get_connectivity(self.device, H, W, K, lab.data_ptr(), counts.data_ptr(), nb.data_ptr(),
+                                                 scratch.data_ptr(), nbytes, torch.cuda.current_stream(dev).cuda_stream))
+        return NodeConnectivity(counts.cpu().numpy(), nb.cpu().numpy().view(np.uint32))
+
+
+def _graph_get_knn_connectivity(self, assignments, num_neighbors):
+    """cfast_slic.pyx:272-281.  Not provided: the reference's fast_slic_knn_connectivity indexes its cell vector with
+    a float expression that overruns it for centres low in the last cell row (fast-slic.cpp:88) -- it crashes on
+    ordinary inputs, so there is no result to reproduce."""
+    raise NotImplementedError("get_knn_connectivity: the reference implementation is out of bounds (fast-slic.cpp:88)")
+
+
+def _graph_get_mask_density(self, mask, assignments):
+    """cfast_slic.pyx:283-302 -> fast_slic_get_mask_density (fast-slic.cpp:141-155): uint8[K]."""
+    assignments = _check_assignments(assignments)
+    mask = np.ascontiguousarray(mask)
+    if mask.dtype != np.uint8 or mask.ndim != 2:
+        raise ValueError("mask must be uint8[H, W]")
+    H, W = assignments.shape
+    if mask.shape[0] != H or mask.shape[1] != W:
+        raise ValueError("The shape of mask does not match the one of assignments")  # cfast_slic.pyx:289-290
+    require_cuda()
+    K = self.num_components
+    dev = torch.device("cuda", self.device)
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        lab = torch.from_numpy(assignments).to(dev)
+        msk = torch.from_numpy(mask).to(dev)
+        cl = torch.from_numpy(np.ascontiguousarray(self._clusters).view(np.uint8)).to(dev)
+        dens = torch.empty(K, dtype=torch.uint8, device=dev)
+        scratch = torch.empty(K, dtype=torch.int32, device=dev)
+        _lib.check(L.fslic_b200_get_mask_density(self.device, H, W, K, cl.data_ptr(), lab.data_ptr(), msk.data_ptr(),
+                                                 dens.data_ptr(), scratch.data_ptr(),
+                                                 torch.cuda.current_stream(dev).cuda_stream))
+        return dens.cpu().numpy()
+
+
+def _graph_broadcast_density_to_mask(self, densities, assignments):
+    """cfast_slic.pyx:304-320 -> fast_slic_cluster_density_to_mask (fast-slic.cpp:157-168): uint8[H, W]."""
+    assignments = _check_assignments(assignments)
+    densities = np.ascontiguousarray(densities)
+    K = self.num_components
+    if densities.dtype != np.uint8 or densities.ndim != 1:
+        raise ValueError("densities must be uint8[K]")
+    if densities.shape[0] != K:
+        raise ValueError("The shape of densities should match the number of clusters")  # cfast_slic.pyx:309-310
+    require_cuda()
+    H, W = assignments.shape
+    dev = torch.device("cuda", self.device)
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        lab = torch.from_numpy(assignments).to(dev)
+        dens = torch.from_numpy(densities).to(dev)
+        out = torch.empty((H, W), dtype=torch.uint8, device=dev)
+        _lib.check(L.fslic_b200_cluster_density_to_mask(self.device, H, W, K, lab.data_ptr(), dens.data_ptr(),
+                                                        out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+        return out.cpu().numpy()
+
+
+SlicModel.get_connectivity = _graph_get_connectivity
+SlicModel.get_knn_connectivity = _graph_get_knn_connectivity
+SlicModel.get_mask_density = _graph_get_mask_density
+SlicModel.broadcast_density_to_mask = _graph_broadcast_density_to_mask
 
 
 class BaseSlic(object):

@@ -10,8 +10,11 @@
 #include <string>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>  // library sort for the adjacency-graph utility only (not on the hot path)
+
 #include "assign.cuh"
 #include "assign5.cuh"
+#include "graph.cuh"
 #include "cca.cuh"
 #include "common.cuh"
 #include "lab.cuh"
@@ -101,6 +104,11 @@ struct fslic_ctx {
     std::vector<cudaEvent_t> pipe_ev;  // [2 * chunks]: input-ready / compute-done events of iterate_host
     // timing
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // the reference's sub-sections of "cca" (cca.cpp:194-263): build_disjoint_set, flatten, threshold_by_area, sort,
+    // substitute, output -- event-timed when collect_timing is on and the batch is not split across streams
+    cudaEvent_t cev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    float cca_ms[6] = {0, 0, 0, 0, 0, 0};
+    bool cca_timing = false, cca_timed = false;
     float stage_ms[FSLIC_T_COUNT] = {0, 0, 0, 0, 0, 0};
     int last_launches = 0;
     int slice = 0;  // first image of the batch slice the front half (Lab + passes) currently works on
@@ -170,6 +178,8 @@ extern "C" int fslic_b200_destroy(fslic_ctx* c) {
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (auto& e : c->ev)
+        if (e) cudaEventDestroy(e);
+    for (auto& e : c->cev)
         if (e) cudaEventDestroy(e);
     for (auto& e : c->kev) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -270,6 +280,7 @@ static int create_impl(int device, int H, int W, int K, int max_batch, bool cca_
     c->heap_K = 65536 + 8;
     CKC(dalloc(&c->heap, bc * (size_t)c->heap_K));
     for (auto& e : c->ev) CKC(cudaEventCreate(&e));
+    for (auto& e : c->cev) CKC(cudaEventCreate(&e));
     CKC(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     CKC(cudaStreamCreateWithFlags(&c->in_stream, cudaStreamNonBlocking));
     CKC(cudaStreamCreateWithFlags(&c->out_stream, cudaStreamNonBlocking));
@@ -376,6 +387,9 @@ static int run_cca(fslic_ctx* c, const uint16_t* d_in, uint16_t* d_out, int batc
         const int nb = (batch - b0 < c->cca_batch) ? (batch - b0) : c->cca_batch;
         const uint16_t* in = d_in + (size_t)b0 * N;
         uint16_t* out = d_out + (size_t)b0 * N;
+        const bool timed = c->cca_timing && nb < 4 && batch <= c->cca_batch;  // one stream, one sub-batch
+        c->cca_timed = timed;
+        if (timed) CK(cudaEventRecord(c->cev[0], st));
         CK(cudaMemsetAsync(c->counters, 0, sizeof(CcaCounters) * nb, st));
         CK(cudaMemsetAsync(c->ahist, 0, sizeof(unsigned int) * CCA_HIST * nb, st));
         dim3 g(cp.nblk, nb);
@@ -391,12 +405,15 @@ static int run_cca(fslic_ctx* c, const uint16_t* d_in, uint16_t* d_out, int batc
                 k_ccl_seams<<<gs, 256, 0, st>>>(cp, in, c->par);
             }
         }
+        if (timed) CK(cudaEventRecord(c->cev[1], st));
         k_ccl_flatten<<<g, 256, 0, st>>>(cp, in, c->par, c->aux, c->blkcnt, c->rootbuf);
         k_scan_blocks<<<nb, 1024, 0, st>>>(c->blkcnt, c->blkoff, cp.nblk, cp.nblk, nullptr, 0, 1,
                                            &c->counters[0].ncomp, (int)(sizeof(CcaCounters) / sizeof(int)), nullptr, -1);
         k_ccl_number<<<dim3(CCA_NUMBER_GRID, nb), CCA_BLOCK, 0, st>>>(cp, c->rootbuf, c->aux, c->blkcnt, c->blkoff, c->cleader, c->carea,
                                                                       c->counters, c->ahist);
+        if (timed) CK(cudaEventRecord(c->cev[2], st));
         k_cca_threshold<<<nb, 1024, 0, st>>>(cp, c->carea, c->counters, c->ahist);
+        if (timed) CK(cudaEventRecord(c->cev[3], st));
         // Everything after the threshold decision depends on the kept set.  For images k_cca_threshold settled
         // that is known now; for the (few) images whose ties need the sequential std::partial_sort replay it
         // is known only after k_cca_select, which keeps a handful of SMs busy for ~1 ms.  So for batches the
@@ -415,11 +432,14 @@ static int run_cca(fslic_ctx* c, const uint16_t* d_in, uint16_t* d_out, int batc
             int ab = ceil_div(N, 256 * 8);
             if (ab > c->num_sms * 8) ab = c->num_sms * 8;
             dim3 ga(ab, nb);
+            if (timed) cudaEventRecord(c->cev[4], ts);
             k_cca_absorb<<<ga, 256, 0, ts>>>(cq, c->par, c->aux, c->cleader, c->cnew, c->counters, c->fin);
+            if (timed) cudaEventRecord(c->cev[5], ts);
             int ob = ceil_div(ceil_div(N, 8), 256);  // 8 pixels per thread on the vector path (any N works: grid-stride)
             if (ob > c->num_sms * 32) ob = c->num_sms * 32;
             dim3 go(ob, nb);
             k_cca_output<<<go, 256, 0, ts>>>(cq, c->par, c->fin, out, c->counters);
+            if (timed) cudaEventRecord(c->cev[6], ts);
         };
         const bool split = nb >= 4;
         const bool early = split && ho && batch <= c->cca_batch && nb <= 64;
@@ -828,6 +848,8 @@ extern "C" int fslic_b200_iterate(fslic_ctx* c, const uint8_t* d_images, fslic_c
     const bool timing = p->collect_timing != 0;
     c->kev_on = p->collect_timing >= 2;
     c->kev_used = 0;
+    c->cca_timing = timing;
+    c->cca_timed = false;
     if (timing) CK(cudaEventRecord(c->ev[0], st));
     rc = iterate_front(c, 0, d_images, d_clusters, batch, p, coef, st, &launches, timing);
     if (rc) return rc;
@@ -844,6 +866,11 @@ extern "C" int fslic_b200_iterate(fslic_ctx* c, const uint8_t* d_images, fslic_c
         CK(cudaEventElapsedTime(&ms, c->ev[2], c->ev[3])); c->stage_ms[FSLIC_T_FULL_ASSIGN] = ms;
         CK(cudaEventElapsedTime(&ms, c->ev[3], c->ev[4])); c->stage_ms[FSLIC_T_CCA] = ms;
         CK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[4])); c->stage_ms[FSLIC_T_TOTAL] = ms;
+        for (int i = 0; i < 6; i++) {
+            c->cca_ms[i] = 0.f;
+            if (c->cca_timed && cudaEventElapsedTime(&ms, c->cev[i], c->cev[i + 1]) == cudaSuccess) c->cca_ms[i] = ms;
+        }
+        cudaGetLastError();
         c->assign_kernel_ms = 0.f;
         c->assign_kernel_launches = 0;
         for (int i = 0; i + 1 < c->kev_used; i += 2) {
@@ -853,6 +880,13 @@ extern "C" int fslic_b200_iterate(fslic_ctx* c, const uint8_t* d_images, fslic_c
         }
     }
     c->last_launches = launches;
+    c->cca_timing = false;
+    return FSLIC_OK;
+}
+
+extern "C" int fslic_b200_cca_stage_ms(fslic_ctx* c, float* out_ms, int count) {
+    if (!c || !out_ms) return set_err(FSLIC_EINVAL, "NULL argument");
+    for (int i = 0; i < count && i < 6; i++) out_ms[i] = c->cca_ms[i];
     return FSLIC_OK;
 }
 
@@ -1135,5 +1169,95 @@ extern "C" int fslic_b200_wait(fslic_ctx* c) {
     CK(cudaStreamSynchronize(c->out_stream));
     CK(cudaStreamSynchronize(c->own_stream));
     c->pending = false;
+    return FSLIC_OK;
+}
+
+// ---- consumers of the label map: stateless, device pointers, caller-provided scratch ------
+static uint32_t conn_table_size(int K) {
+    uint32_t t = 4096;
+    while (t < 32u * (uint32_t)K) t <<= 1;  // a superpixel map has ~3 distinct adjacent pairs per label
+    return t;
+}
+static size_t conn_sort_temp_bytes(uint32_t T) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                    (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)T);
+    return bytes;
+}
+
+extern "C" size_t fslic_b200_connectivity_scratch_bytes(int K) {
+    if (K <= 0) return 256;
+    const size_t T = conn_table_size(K);
+    return align_up(T * 4, 256) * 2 + align_up(T * 8, 256) * 2 + align_up(conn_sort_temp_bytes((uint32_t)T), 256) + 256;
+}
+
+extern "C" int fslic_b200_get_connectivity(int device, int H, int W, int K, const uint16_t* d_labels, int32_t* d_counts,
+                                           uint32_t* d_neighbors, void* d_scratch, size_t scratch_bytes, void* stream) {
+    if (H <= 0 || W <= 0 || K <= 0 || K > 65535) return set_err(FSLIC_EINVAL, "bad H, W or K");
+    if (!d_labels || !d_counts || !d_neighbors || !d_scratch) return set_err(FSLIC_EINVAL, "NULL argument");
+    if (scratch_bytes < fslic_b200_connectivity_scratch_bytes(K)) return set_err(FSLIC_EINVAL, "scratch too small");
+    USE_DEVICE(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint32_t T = conn_table_size(K);
+    unsigned char* p = static_cast<unsigned char*>(d_scratch);
+    uint32_t* tkey = reinterpret_cast<uint32_t*>(p); p += align_up((size_t)T * 4, 256);
+    uint32_t* skey = reinterpret_cast<uint32_t*>(p); p += align_up((size_t)T * 4, 256);
+    unsigned long long* tord = reinterpret_cast<unsigned long long*>(p); p += align_up((size_t)T * 8, 256);
+    unsigned long long* sord = reinterpret_cast<unsigned long long*>(p); p += align_up((size_t)T * 8, 256);
+    size_t temp_bytes = conn_sort_temp_bytes(T);
+    void* temp = p; p += align_up(temp_bytes, 256);
+    int* overflow = reinterpret_cast<int*>(p);
+    CK(cudaMemsetAsync(tkey, 0xff, (size_t)T * 4, st));
+    CK(cudaMemsetAsync(tord, 0xff, (size_t)T * 8, st));
+    CK(cudaMemsetAsync(overflow, 0, 4, st));
+    CK(cudaMemsetAsync(d_counts, 0, (size_t)K * 4, st));
+    CK(cudaMemsetAsync(d_neighbors, 0, (size_t)K * CONN_MAX * 4, st));
+    if (H > 1 && W > 1) {
+        const long n = (long)(H - 1) * (W - 1);
+        long blocks = (n + 255) / 256;
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        k_conn_discover<<<(int)blocks, 256, 0, st>>>(d_labels, H, W, K, tkey, tord, T - 1, overflow);
+        int h_overflow = 0;
+        CK(cudaMemcpyAsync(&h_overflow, overflow, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (h_overflow) {
+            k_conn_scan<<<1, 32, 0, st>>>(d_labels, H, W, K, d_counts, d_neighbors);
+        } else {
+            if (cub::DeviceRadixSort::SortPairs(temp, temp_bytes, tord, sord, tkey, skey, (int)T, 0, 64, st) != cudaSuccess)
+                return set_err(FSLIC_ECUDA, "radix sort of the pair table failed");
+            k_conn_walk<<<1, 32, 0, st>>>(sord, skey, T, K, d_counts, d_neighbors);
+        }
+    }
+    CK(cudaGetLastError());
+    return FSLIC_OK;
+}
+
+extern "C" int fslic_b200_get_mask_density(int device, int H, int W, int K, const fslic_cluster* d_clusters,
+                                           const uint16_t* d_labels, const uint8_t* d_mask, uint8_t* d_densities,
+                                           int32_t* d_scratch, void* stream) {
+    if (H <= 0 || W <= 0 || K <= 0 || K > 65535) return set_err(FSLIC_EINVAL, "bad H, W or K");
+    if (!d_clusters || !d_labels || !d_mask || !d_densities || !d_scratch) return set_err(FSLIC_EINVAL, "NULL argument");
+    USE_DEVICE(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long n = (long)H * W;
+    CK(cudaMemsetAsync(d_scratch, 0, (size_t)K * 4, st));
+    long blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_mask_sum<<<(int)blocks, 256, 0, st>>>(d_labels, d_mask, n, K, d_scratch);
+    k_density_final<<<ceil_div(K, 256), 256, 0, st>>>(d_scratch, d_clusters, K, d_densities);
+    CK(cudaGetLastError());
+    return FSLIC_OK;
+}
+
+extern "C" int fslic_b200_cluster_density_to_mask(int device, int H, int W, int K, const uint16_t* d_labels,
+                                                  const uint8_t* d_densities, uint8_t* d_result, void* stream) {
+    if (H <= 0 || W <= 0 || K <= 0 || K > 65535) return set_err(FSLIC_EINVAL, "bad H, W or K");
+    if (!d_labels || !d_densities || !d_result) return set_err(FSLIC_EINVAL, "NULL argument");
+    USE_DEVICE(device);
+    const long n = (long)H * W;
+    long blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_density_broadcast<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(d_labels, d_densities, n, K, d_result);
+    CK(cudaGetLastError());
     return FSLIC_OK;
 }

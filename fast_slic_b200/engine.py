@@ -165,6 +165,11 @@ class Engine:
         check(self._L.fslic_b200_stage_ms(self._h, out, 6))
         return dict(zip(_lib.STAGE_NAMES, [float(v) for v in out]))
 
+    def cca_stage_ms(self):
+        out = (C.c_float * 6)()
+        check(self._L.fslic_b200_cca_stage_ms(self._h, out, 6))
+        return dict(zip(_lib.CCA_STAGE_NAMES, [float(v) for v in out]))
+
     def assign_kernel_time(self):
         """(total ms, launches) of the fused assign+update kernel in the last iterate (collect_timing=2)."""
         ms, n = C.c_float(), C.c_int()

@@ -18,6 +18,7 @@
 #ifndef FSLIC_B200_H
 #define FSLIC_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -112,6 +113,21 @@ int fslic_b200_wait(fslic_ctx* ctx);
 int fslic_b200_enforce_connectivity(fslic_ctx* ctx, uint16_t* d_labels, int batch, int K, int min_threshold,
                                     void* stream);
 
+/* == fast_slic_get_connectivity (src/fast-slic.cpp:16-78; cfast_slic.pyx:262-270): the superpixel adjacency graph of
+ *    one label map d_labels u16[H*W] -> d_counts int32[K], d_neighbors u32[K*12] (row k: the first d_counts[k] entries,
+ *    in the order the reference's raster scan links them; at most 12 per label, like the reference).  Stateless:
+ *    d_scratch must hold fslic_b200_connectivity_scratch_bytes(K) bytes.  Synchronises `stream` once. */
+size_t fslic_b200_connectivity_scratch_bytes(int K);
+int fslic_b200_get_connectivity(int device, int H, int W, int K, const uint16_t* d_labels, int32_t* d_counts,
+                                uint32_t* d_neighbors, void* d_scratch, size_t scratch_bytes, void* stream);
+
+/* == fast_slic_get_mask_density / fast_slic_cluster_density_to_mask (src/fast-slic.cpp:141-168; cfast_slic.pyx:283-320).
+ *    d_mask u8[H*W], d_densities u8[K]; d_scratch int32[K].  Asynchronous on `stream`. */
+int fslic_b200_get_mask_density(int device, int H, int W, int K, const fslic_cluster* d_clusters, const uint16_t* d_labels,
+                                const uint8_t* d_mask, uint8_t* d_densities, int32_t* d_scratch, void* stream);
+int fslic_b200_cluster_density_to_mask(int device, int H, int W, int K, const uint16_t* d_labels, const uint8_t* d_densities,
+                                       uint8_t* d_result, void* stream);
+
 /* Stage probes for the parity tests (the reference's protected quad_image / assignment,
  * context.h:48-50): copies of the last iterate()'s Lab quad image [B,H,W,4] u8 and pre-CCA
  * labels [B,H,W] u16 into caller device buffers (either may be NULL). */
@@ -136,6 +152,11 @@ int fslic_b200_debug_cca_counters(fslic_ctx* ctx, int32_t* out8, int image);
 
 /* Milliseconds spent per stage in the last iterate() with collect_timing != 0. */
 int fslic_b200_stage_ms(fslic_ctx* ctx, float* out_ms, int count);
+
+/* Milliseconds of the connectivity stage's sub-sections in the last iterate() with collect_timing != 0 and fewer than
+ * 4 images, in the reference's order and names (cca.cpp:194-263): build_disjoint_set, flatten, threshold_by_area,
+ * sort, substitute, output.  Zeros when the stage was not timed (larger batches overlap the tail on a side stream). */
+int fslic_b200_cca_stage_ms(fslic_ctx* ctx, float* out_ms, int count);
 
 /* Geometry queries (S = (int16)sqrt(H*W/K), context.h:60; number of kernel launches per iterate). */
 int fslic_b200_get_S(const fslic_ctx* ctx);

@@ -353,6 +353,10 @@ def test_python_surface_matches_reference_api():
     import json
     rep = json.loads(slic.slic_model.last_timing_report)
     assert rep["name"] == "iterate" and len(rep["children"]) == 5
+    cca = rep["children"][4]["children"][0]   # enforce_connectivity -> cca -> the reference's six sub-sections
+    assert cca["name"] == "cca" and [c["name"] for c in cca["children"]] == [
+        "build_disjoint_set", "flatten", "threshold_by_area", "sort", "substitute", "output"]
+    assert sum(c["duration"] for c in cca["children"]) > 0
 
 
 def test_single_image_api_parity(checker):
@@ -367,3 +371,44 @@ def test_single_image_api_parity(checker):
     got2 = s.iterate(img).view(np.uint16)  # warm start
     want2 = checker.iterate(img, cl, 10, 10.0, 0.1, 3, True)
     assert (got2 == want2).all()
+
+
+@pytest.mark.parametrize("H,W,K,kind,msf", [(120, 160, 48, "syn", 0.25), (97, 131, 37, "noise", 0.0), (200, 300, 150, "blocks", 0.0),
+                                            (64, 64, 1500, "noise", 0.0), (480, 640, 200, "syn", 0.1), (720, 1280, 1600, "syn", 0.0)])
+def test_graph_and_density_consumers(checker, H, W, K, kind, msf):
+    """SlicModel.get_connectivity / get_mask_density / broadcast_density_to_mask (cfast_slic.pyx:262-320) on the GPU ==
+    the reference's fast-slic.cpp functions, exactly (neighbour ORDER included; the 12-neighbour cap is exercised by the
+    msf = 0 and the synthetic saturated maps)."""
+    from fast_slic_b200 import Slic
+    img = make_image(kind, H, W, seed=17)
+    s = Slic(num_components=K, min_size_factor=msf)
+    lab = s.iterate(img)
+    m = s.slic_model
+    assert m.get_connectivity(lab).tolist() == checker.get_connectivity(lab.view(np.uint16), K)
+    raw = (make_image("noise", H, W, seed=3)[..., 0].astype(np.uint16) % min(K, 40)).astype(np.uint16).view(np.int16)
+    assert m.get_connectivity(np.ascontiguousarray(raw)).tolist() == checker.get_connectivity(raw.view(np.uint16), K)
+    mask = np.ascontiguousarray(make_image("syn", H, W, seed=5)[..., 1])
+    cl = m.cluster_array
+    dens = m.get_mask_density(mask, lab)
+    assert (dens == checker.get_mask_density(cl, lab.view(np.uint16), mask)).all()
+    holes = lab.copy()
+    holes[::7, ::5] = -1
+    assert (m.get_mask_density(mask, holes) == checker.get_mask_density(cl, holes.view(np.uint16), mask)).all()
+    assert (m.broadcast_density_to_mask(dens, holes) == checker.density_to_mask(K, holes.view(np.uint16), dens)).all()
+    with pytest.raises(ValueError):
+        m.get_mask_density(mask[:-1], lab)
+    with pytest.raises(ValueError):
+        m.broadcast_density_to_mask(dens[:-1], lab)
+    with pytest.raises(NotImplementedError):
+        m.get_knn_connectivity(lab, 4)
+
+
+def test_connectivity_table_overflow_falls_back_to_the_scan(checker):
+    """A label map with far more distinct adjacent pairs than a superpixel map has: the pair table overflows and the
+    single-thread replay of the reference's loop takes over (exact, slow)."""
+    from fast_slic_b200 import SlicModel
+    H, W, K = 256, 256, 3000   # ~196 000 distinct adjacent pairs > the 131 072-entry table of K = 3000
+    rng = np.random.RandomState(9)
+    lab = rng.randint(0, K, (H, W)).astype(np.uint16).view(np.int16)
+    m = SlicModel(K)
+    assert m.get_connectivity(lab).tolist() == checker.get_connectivity(lab.view(np.uint16), K)
