@@ -412,3 +412,20 @@ def test_connectivity_table_overflow_falls_back_to_the_scan(checker):
     lab = rng.randint(0, K, (H, W)).astype(np.uint16).view(np.int16)
     m = SlicModel(K)
     assert m.get_connectivity(lab).tolist() == checker.get_connectivity(lab.view(np.uint16), K)
+
+
+def test_stream_warm_start_is_the_reference_second_iterate(checker):
+    """SlicStream(warm_start=True): image b of batch t+1 starts from the clusters image b of batch t ended with ==
+    calling the reference's iterate() again on the same model (cfast_slic.pyx:160 keeps the clusters)."""
+    from fast_slic_b200 import SlicStream
+    H, W, K, B, T = 120, 160, 40, 3, 4
+    frames = [np.stack([make_image("syn", H, W, seed=500 + 10 * b + t, sigma=10.0 + t) for b in range(B)]) for t in range(T)]
+    st = SlicStream(H, W, K, batch=B, depth=2, min_size_factor=0.1, warm_start=True)
+    got = list(st.map(frames))
+    assert len(got) == T and st.in_flight == 0
+    for b in range(B):
+        cl = checker.initialize(frames[0][b], K)
+        for t in range(T):
+            want = checker.iterate(frames[t][b], cl, 10, 10.0, 0.1, 3, True)   # cl carries over, like the reference
+            assert (got[t][b].view(np.uint16) == want).all(), (b, t)
+    st.close()
