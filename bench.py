@@ -455,7 +455,8 @@ def main():
                 done.record(st)
             with torch.cuda.stream(comm):
                 comm.wait_event(done)
-                dist.all_gather_into_tensor(gbuf[i % NCTX].view(-1), lab.view(-1))
+                # raw bytes on the wire: NCCL's process group has no int16, and the labels are opaque u16 anyway
+                dist.all_gather_into_tensor(gbuf[i % NCTX].view(torch.uint8).view(-1), lab.view(torch.uint8).view(-1))
                 ev = torch.cuda.Event()
                 ev.record(comm)
                 drained[i % NCTX] = ev
