@@ -115,6 +115,14 @@ __device__ __forceinline__ void a5_tma_store_3d(const CUtensorMap* map, uint32_t
 __device__ __forceinline__ void a5_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void a5_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// prmt.b32, generic mode: result byte i = byte (sel nibble i & 7) of {a, b}, or that byte's sign replicated when the
+// nibble's bit 3 is set
+__device__ __forceinline__ uint32_t a5_prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+
 // per-byte equality of two words whose bytes are all below 0x80 -> 0x80 in every equal byte (3 logic ops)
 __device__ __forceinline__ uint32_t eq7(uint32_t w, uint32_t m) { return ~((w ^ m) + 0x7f7f7f7fu) & 0x80808080u; }
 
@@ -372,7 +380,8 @@ __global__ void __launch_bounds__(32 * A5_MAXWARPS, 1)
             a5_sts16<A5_OFF_LAB + 2 * BW * 2>(ll, a5_lds16<A5_OFF_TK>(tk + rb2 * 2));
             a5_sts16<A5_OFF_LAB + 3 * BW * 2>(ll, a5_lds16<A5_OFF_TK>(tk + rb3 * 2));
             const uint32_t rw = __byte_perm(__byte_perm(rb0, rb1, 0x3340), __byte_perm(rb2, rb3, 0x3340), 0x5410);
-            if (!__all_sync(FSLIC_FULL, max(max(best0, best1), max(best2, best3)) < A5_BIGKEY)) slow = true;
+            const bool tile_cov = __all_sync(FSLIC_FULL, max(max(best0, best1), max(best2, best3)) < A5_BIGKEY);
+            if (!tile_cov) slow = true;
 
             // ---- 4. update sums on the tensor cores (context.cpp:316-327) ----
             if (UPDATE) {
@@ -392,11 +401,44 @@ __global__ void __launch_bounds__(32 * A5_MAXWARPS, 1)
                 const uint32_t flo = tig == 1 ? (uint32_t)tj0 : 0u, fhi = tig == 0 ? (uint32_t)wi0 : 0u;
                 const uint32_t fmul = tig == 0 ? (uint32_t)stride : 1u;
                 const int n16 = (n_t + 15) >> 4;
+                // Common case (every pixel of the tile covered, at most 16 candidates): the ranks fit a nibble, and ONE
+                // PRMT turns four of them into the one-hot bytes of candidate row g -- the selector nibble picks byte
+                // (rank & 7) of an 8-byte pool that holds 0x80 at position g only, and its bit 3 (rank >= 8) replicates
+                // that byte's sign: 0x80 <=> rank == g, 0xFF <=> rank == g + 8, 0 otherwise.
+                const bool nib = tile_cov && n_t <= 16;
+                uint32_t rw16 = 0, plo = 0, phi = 0;
+                if (nib) {
+                    rw16 = __byte_perm(rw | (rw >> 4), 0u, 0x4420);
+                    plo = g < 4 ? (0x80u << (8 * g)) : 0u;
+                    phi = g >= 4 ? (0x80u << (8 * (g - 4))) : 0u;
+                }
                 for (int nt = 0; nt < n16; nt++) {
                     int d[4] = {0, 0, 0, 0};
                     const uint32_t mg0 = (uint32_t)(nt * 16 + (int)g) * 0x01010101u, mg1 = mg0 + 0x08080808u;
                     const bool two = n_t > nt * 16 + 8;  // candidates g + 8 exist in this pass
-                    if (two) {
+                    if (nib) {
+#define A5_MMAN(s4)                                                                                         \
+    {                                                                                                       \
+        const uint32_t w0 = __shfl_sync(FSLIC_FULL, rw16, 8 * s4 + tig), w1 = __shfl_sync(FSLIC_FULL, rw16, 8 * s4 + 4 + tig); \
+        const uint32_t r0 = a5_prmt(plo, phi, w0), r1 = a5_prmt(plo, phi, w1);                              \
+        const uint32_t t0 = r0 + r0, t1 = r1 + r1;                                                          \
+        mma_u8_16x8x32(d, r0 & ~t0 & 0x80808080u, t0 & 0x80808080u, r1 & ~t1 & 0x80808080u, t1 & 0x80808080u, \
+                       a5_lds32<A5_OFF_SCR + 256 * s4>(fb), a5_lds32<A5_OFF_SCR + 256 * s4 + 128>(fb));     \
+    }
+#define A5_MMAN1(s4)                                                                                        \
+    {                                                                                                       \
+        const uint32_t w0 = __shfl_sync(FSLIC_FULL, rw16, 8 * s4 + tig), w1 = __shfl_sync(FSLIC_FULL, rw16, 8 * s4 + 4 + tig); \
+        mma_u8_16x8x32(d, a5_prmt(plo, phi, w0), 0u, a5_prmt(plo, phi, w1), 0u,                             \
+                       a5_lds32<A5_OFF_SCR + 256 * s4>(fb), a5_lds32<A5_OFF_SCR + 256 * s4 + 128>(fb));     \
+    }
+                        if (two) {
+                            A5_MMAN(0) A5_MMAN(1) A5_MMAN(2) A5_MMAN(3)
+                        } else {  // all ranks below 8: the selected byte is the one-hot byte itself
+                            A5_MMAN1(0) A5_MMAN1(1) A5_MMAN1(2) A5_MMAN1(3)
+                        }
+#undef A5_MMAN
+#undef A5_MMAN1
+                    } else if (two) {
 #define A5_MMA2(s4)                                                                                         \
     {                                                                                                       \
         const uint32_t w0 = __shfl_sync(FSLIC_FULL, rw, 8 * s4 + tig), w1 = __shfl_sync(FSLIC_FULL, rw, 8 * s4 + 4 + tig); \
