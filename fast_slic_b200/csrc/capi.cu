@@ -422,7 +422,13 @@ static int run_cca(fslic_ctx* c, const uint16_t* d_in, uint16_t* d_out, int batc
         auto tail = [&](int which, cudaStream_t ts) {
             CcaParams cq = cp;
             cq.which = which;
-            k_kept_rank<<<nb, 1024, 0, ts>>>(cq, c->carea, c->counters, c->cnew);
+            const dim3 gk(cp.nblk < CCA_KEPT_GRID ? cp.nblk : CCA_KEPT_GRID, nb);
+            k_kept_count<<<gk, CCA_BLOCK, 0, ts>>>(cq, c->carea, c->counters, c->blkcnt);
+            k_scan_blocks<<<nb, 1024, 0, ts>>>(c->blkcnt, c->blkoff, cp.nblk, 0, &c->counters[0].ncomp,
+                                               (int)(sizeof(CcaCounters) / sizeof(int)), CCA_BLOCK,
+                                               &c->counters[0].nkept, (int)(sizeof(CcaCounters) / sizeof(int)),
+                                               c->counters, which);
+            k_kept_label<<<gk, CCA_BLOCK, 0, ts>>>(cq, c->carea, c->counters, c->blkoff, c->cnew);
             int ab = ceil_div(N, 256 * 8);
             if (ab > c->num_sms * 8) ab = c->num_sms * 8;
             dim3 ga(ab, nb);
@@ -476,10 +482,10 @@ static int run_cca(fslic_ctx* c, const uint16_t* d_in, uint16_t* d_out, int batc
         }
         if (split) {
             CK(cudaStreamWaitEvent(st, c->side_join, 0));
-            if (launches) *launches += 3;
+            if (launches) *launches += 5;
         }
         CK(cudaGetLastError());
-        if (launches) *launches += 10;
+        if (launches) *launches += 12;
     }
     return FSLIC_OK;
 }

@@ -991,66 +991,6 @@ __global__ void __launch_bounds__(CCA_BLOCK) k_kept_label(CcaParams cp, const ui
     }
 }
 
-// k_kept_count + k_scan_blocks + k_kept_label in one launch: one CTA per image walks the components in order, 4 per
-// thread, carrying the running number of kept components (new label = rank among the kept ones, cca.cpp:229-237;
-// 0xFFFF for components that must be absorbed).  Three dependent launches -> one; the walk is 90 steps for a 720p
-// image with 3.7e5 components.
-__global__ void __launch_bounds__(1024) k_kept_rank(CcaParams cp, const uint32_t* __restrict__ carea_all,
-                                                    CcaCounters* __restrict__ counters, uint16_t* __restrict__ cnew_all) {
-    __shared__ int s_warp[32];
-    __shared__ int s_base;
-    const int b = blockIdx.x;
-    if (cca_skip_image(cp, &counters[b])) return;
-    const int ncomp = counters[b].ncomp;
-    const int sel_mode = counters[b].sel_mode, keep_thres = counters[b].keep_thres;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t* area = carea_all + (size_t)b * cp.N;
-    uint16_t* cnew = cnew_all + (size_t)b * cp.N;
-    if (tid == 0) s_base = 0;
-    __syncthreads();
-    for (int base = 0; base < ncomp; base += 4096) {
-        const int c0 = base + tid * 4;
-        bool k[4];
-        int cnt = 0;
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            k[u] = (c0 + u < ncomp) && cca_is_kept(area[c0 + u], sel_mode, keep_thres);
-            cnt += k[u];
-        }
-        int x = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int y = __shfl_up_sync(FSLIC_FULL, x, o);
-            if (lane >= o) x += y;
-        }
-        if (lane == 31) s_warp[warp] = x;
-        __syncthreads();
-        const int carry = s_base;
-        if (warp == 0) {
-            const int w = s_warp[lane];
-            int z = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int y = __shfl_up_sync(FSLIC_FULL, z, o);
-                if (lane >= o) z += y;
-            }
-            s_warp[lane] = z - w;
-            if (lane == 31) s_base = carry + z;  // read by everybody only after the next barrier
-        }
-        __syncthreads();
-        int r = carry + s_warp[warp] + x - cnt;
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            if (c0 + u < ncomp) {
-                cnew[c0 + u] = k[u] ? (uint16_t)r : (uint16_t)0xFFFF;
-                r += k[u];
-            }
-        }
-        __syncthreads();  // s_warp is rewritten by the next round
-    }
-    if (tid == 0) counters[b].nkept = s_base;
-}
-
 // final label of every component, written at its leader pixel (cca.cpp:238-255)
 __global__ void __launch_bounds__(256) k_cca_absorb(CcaParams cp, const int* __restrict__ par_all,
                                                     const uint32_t* __restrict__ aux_all,
