@@ -147,6 +147,128 @@ __global__ void __launch_bounds__(1024) k_prepare(PrepParams pp, fslic_cluster* 
 }
 
 // ---------------------------------------------------------------------------------------------
+// k_prepare2: the same bookkeeping spread over ceil(K / 256) CTAs per image (round 2).  k_prepare is one CTA per image
+// and latency bound -- two clusters per thread one after the other, five block barriers -- 13 us per launch, eleven
+// launches per iterate: a third of a single image's device time.  Here every cluster has its own thread (steps 1-3 of
+// k_prepare: finalise, re-seed, clamp, CInfo record, cell histogram through global atomics), and the LAST CTA of an
+// image to finish (ticket counter) runs step 4 for the whole image: cell histogram -> shared memory, exclusive scan,
+// scatter of the records.  The histogram and the ticket are left zeroed for the next launch.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_prepare2(PrepParams pp, fslic_cluster* __restrict__ clusters,
+                                                  unsigned long long* __restrict__ acc, const uint32_t* __restrict__ quad,
+                                                  CInfo* __restrict__ cinfo, int* __restrict__ cell_start,
+                                                  CInfo* __restrict__ cinfo_tmp, int* __restrict__ cell_cnt,
+                                                  unsigned int* __restrict__ tickets) {
+    extern __shared__ int s_cnt[];  // last CTA only: ncell + 1 counters
+    __shared__ int s_warp[8];
+    __shared__ bool s_last;
+    const int b = blockIdx.y;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    fslic_cluster* cl = clusters + (size_t)b * pp.K;
+    unsigned long long* ac = acc + (size_t)b * pp.K * 4;
+    const uint32_t* qd = quad + (size_t)b * pp.H * pp.W;
+    CInfo* ci = cinfo_tmp + (size_t)b * pp.K;          // by cluster index (scratch)
+    CInfo* ci_sorted = cinfo + (size_t)b * pp.K;       // by cell, what the assign kernels read
+    int* cs = cell_start + (size_t)b * (pp.ncell + 1);
+    int* gcnt = cell_cnt + (size_t)b * (pp.ncell + 1);
+
+    const int k = blockIdx.x * nt + tid;
+    if (k < pp.K) {
+        fslic_cluster c = cl[k];
+        if (pp.finalize) {
+            // packed sums: [0] = n | sum_y << 32, [1] = sum_x | sum_L << 32, [2] = sum_a | sum_b << 32
+            const unsigned long long w0 = ac[k * 4 + 0], w1 = ac[k * 4 + 1], w2 = ac[k * 4 + 2];
+            const uint32_t n = (uint32_t)w0;
+            c.num_members = n;  // written even when n == 0 (context.cpp:360-362)
+            if (n > 0) {
+                const int32_t in = (int32_t)n, half = in / 2;
+                c.y = (float)(((int32_t)(w0 >> 32) + half) / in);
+                c.x = (float)(((int32_t)(uint32_t)w1 + half) / in);
+                c.r = (float)(((int32_t)(w1 >> 32) + half) / in);
+                c.g = (float)(((int32_t)(uint32_t)w2 + half) / in);
+                c.b = (float)(((int32_t)(w2 >> 32) + half) / in);
+            }
+            ac[k * 4 + 0] = 0; ac[k * 4 + 1] = 0; ac[k * 4 + 2] = 0;
+        }
+        if (pp.first) {
+            int y = min(max((int)c.y, 0), pp.H - 1), x = min(max((int)c.x, 0), pp.W - 1);
+            const uint32_t q = qd[(size_t)y * pp.W + x];
+            c.r = (float)(q & 0xff);
+            c.g = (float)((q >> 8) & 0xff);
+            c.b = (float)((q >> 16) & 0xff);
+        }
+        // safeguard clamp, stored back like the reference does
+        c.x = fminf(fmaxf(c.x, 0.f), (float)(pp.W - 1));
+        c.y = fminf(fmaxf(c.y, 0.f), (float)(pp.H - 1));
+        c.number = (uint16_t)k;
+        c.is_active = 1;
+        c.is_updatable = 2;
+        cl[k] = c;
+
+        const int cy = (int16_t)c.y, cx = (int16_t)c.x;
+        const int cr = (int16_t)c.r, cg = (int16_t)c.g, cb = (int16_t)c.b;
+        const int phase = 2 * ((cy / pp.T) & 1) + ((cx / pp.T) & 1);
+        CInfo r;
+        r.cyx = (cy & 0xffff) | (cx << 16);
+        r.color = (uint32_t)(cr & 0xff) | ((uint32_t)(cg & 0xff) << 8) | ((uint32_t)(cb & 0xff) << 16);
+        r.sortkey = ((uint32_t)phase << 16) | (uint32_t)k;
+        r.pad = 0;
+        ci[k] = r;
+        atomicAdd(&gcnt[(cy / pp.G) * pp.cellW + (cx / pp.G)], 1);
+    }
+    // the last CTA of this image to get here sorts the records into the cell grid
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(&tickets[b], 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int ncnt = pp.ncell + 1;
+    for (int c = tid; c < ncnt; c += nt) {
+        s_cnt[c] = __ldcg(&gcnt[c]);
+        gcnt[c] = 0;  // ready for the next launch
+    }
+    if (tid == 0) tickets[b] = 0;
+    __syncthreads();
+    {   // exclusive scan: every thread owns a run of consecutive cells, one block-wide scan of the run totals
+        const int per = (ncnt + nt - 1) / nt;
+        const int c0 = tid * per;
+        int local = 0;
+        for (int u = 0; u < per; u++) {
+            const int c = c0 + u;
+            if (c < ncnt) local += s_cnt[c];
+        }
+        int x = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int y = __shfl_up_sync(FSLIC_FULL, x, o);
+            if ((tid & 31) >= o) x += y;
+        }
+        if ((tid & 31) == 31) s_warp[tid >> 5] = x;
+        __syncthreads();
+        int woff = 0;
+        for (int w = 0; w < (tid >> 5); w++) woff += s_warp[w];
+        int run = woff + x - local;  // exclusive prefix of this thread's first cell
+        for (int u = 0; u < per; u++) {
+            const int c = c0 + u;
+            if (c < ncnt) {
+                const int v = s_cnt[c];
+                s_cnt[c] = run;  // becomes the running fill pointer
+                cs[c] = run;
+                run += v;
+            }
+        }
+    }
+    __syncthreads();
+    for (int kk = tid; kk < pp.K; kk += nt) {
+        const uint4 r = __ldcg(reinterpret_cast<const uint4*>(&ci[kk]));  // written by other CTAs: read through L2
+        const int cy = (int16_t)(r.x & 0xffff), cx = (int)r.x >> 16;
+        const int slot = atomicAdd(&s_cnt[(cy / pp.G) * pp.cellW + (cx / pp.G)], 1);
+        *reinterpret_cast<uint4*>(&ci_sorted[slot]) = r;  // order inside a cell is arbitrary: consumers rank by sortkey
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Spatial patch (BaseContext::set_spatial_patch, context.cpp:23-40), laid out for LINEAR addressing:
 //   tbl[(di + OY) * TS + (dj + OX)] = (u16)(coef * (float)(|di| + |dj|))  inside the (2S+1)^2 window,
 //                                   = FSLIC_BIGSP                         outside it,

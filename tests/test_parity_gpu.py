@@ -429,3 +429,32 @@ def test_stream_warm_start_is_the_reference_second_iterate(checker):
             want = checker.iterate(frames[t][b], cl, 10, 10.0, 0.1, 3, True)   # cl carries over, like the reference
             assert (got[t][b].view(np.uint16) == want).all(), (b, t)
     st.close()
+
+
+def test_graph_replay_device_api_rotating_images(checker):
+    """fslic_b200_iterate with fewer than 4 images: from the second call with the same cluster / label buffers and
+    parameters everything after the Lab kernel is a replayed CUDA graph, whatever image buffer comes in (a video stream).
+    Four frames per stream, two streams of images in one batch, on a non-default stream; warm start across frames."""
+    from fast_slic_b200 import Engine
+    H, W, K, B, T = 120, 160, 40, 2, 5
+    eng = Engine(H, W, K, B)
+    p = eng.params(10.0, 0.1, 3, True, 10)
+    frames = [np.stack([make_image("syn" if (t + b) % 2 else "noise", H, W, seed=700 + 10 * b + t) for b in range(B)])
+              for t in range(T)]
+    d_frames = [torch.from_numpy(f).cuda() for f in frames]       # a different device buffer every call
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        cl = eng.initialize_clusters(d_frames[0])
+        lab = torch.empty((B, H, W), dtype=torch.int16, device="cuda")
+        outs = []
+        for t in range(T):
+            eng.iterate(d_frames[t], cl, p, lab)
+            outs.append((lab.clone(), cl.clone()))
+    st.synchronize()
+    for b in range(B):
+        c0 = checker.initialize(frames[0][b], K)
+        for t in range(T):
+            want = checker.iterate(frames[t][b], c0, 10, 10.0, 0.1, 3, True)   # clusters carry over (warm start)
+            assert (outs[t][0][b].cpu().numpy().view(np.uint16) == want).all(), (b, t)
+            assert outs[t][1][b].cpu().numpy().tobytes() == c0.tobytes(), (b, t)
+    eng.close()
