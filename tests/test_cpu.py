@@ -298,3 +298,36 @@ def test_gloo_world_size_2_gather(tmp_path):
                        capture_output=True, text=True, timeout=240, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("ok") == 2
+
+
+def _build_cython_stub(tmp_path):
+    pytest.importorskip("Cython")
+    if not os.path.exists(os.path.join(ROOT, "fast_slic_b200", "libfslic_b200.so")):
+        pytest.skip("libfslic_b200.so not built")
+    subprocess.check_call(["bash", os.path.join(ROOT, "integration", "build_stub.sh"), str(tmp_path)],
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    sys.path.insert(0, str(tmp_path))
+    try:
+        import importlib
+        return importlib.import_module("cfast_slic_b200")
+    finally:
+        sys.path.pop(0)
+
+
+def test_cython_stub_builds_and_binds(tmp_path):
+    """INTEGRATION.md section 2 for real: the Cython branch a maintainer of the reference would add compiles against
+    include/fslic_b200.h, links libfslic_b200.so, keeps the reference's signatures / exception types, and -- on this
+    GPU-less box -- fails loudly instead of falling back to anything."""
+    m = _build_cython_stub(tmp_path)
+    assert m.sizeof_cluster() == 32
+    with pytest.raises(ValueError):
+        m.SlicModelCuda(70000)
+    model = m.SlicModelCuda(50)
+    with pytest.raises(RuntimeError):                       # cfast_slic.pyx:151
+        model.iterate(np.zeros((48, 64, 3), np.uint8), 10, 10.0, 0.25, 3)
+    with pytest.raises(ValueError):                         # cfast_slic.pyx:125
+        model.initialize(np.zeros((48, 64, 4), np.uint8))
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            model.initialize(np.zeros((48, 64, 3), np.uint8))

@@ -458,3 +458,29 @@ def test_graph_replay_device_api_rotating_images(checker):
             assert (outs[t][0][b].cpu().numpy().view(np.uint16) == want).all(), (b, t)
             assert outs[t][1][b].cpu().numpy().tobytes() == c0.tobytes(), (b, t)
     eng.close()
+
+
+def test_cython_stub_parity(checker, tmp_path):
+    """The reference-side Cython binding of INTEGRATION.md section 2 (integration/cfast_slic_b200.pyx), built on the box
+    and driven like cfast_slic.SlicModel: same labels and clusters as the compiled reference, cold and warm start."""
+    import importlib, os, subprocess, sys
+    pytest.importorskip("Cython")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["bash", os.path.join(root, "integration", "build_stub.sh"), str(tmp_path)],
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    sys.path.insert(0, str(tmp_path))
+    try:
+        m = importlib.import_module("cfast_slic_b200")
+    finally:
+        sys.path.pop(0)
+    img = make_image("syn", 240, 320, seed=61)
+    model = m.SlicModelCuda(120)
+    model.convert_to_lab = True
+    model.initialize(img)
+    cl = checker.initialize(img, 120)
+    for _ in range(2):
+        got = model.iterate(img, 10, 10.0, 0.1, 3)
+        want = checker.iterate(img, cl, 10, 10.0, 0.1, 3, True)
+        assert got.dtype == np.int16 and (got.view(np.uint16) == want).all()
+        for k, c in enumerate(model.clusters):
+            assert c["number"] == k and c["yx"] == (float(cl[k]["y"]), float(cl[k]["x"])) and c["num_members"] == int(cl[k]["num_members"])
