@@ -184,8 +184,10 @@ class SlicModel(object):
         return self._clusters
 
     def _unsupported(self):
-        if self.real_dist:
-            raise NotImplementedError("float-distance variants (real_dist) are outside the CUDA hot path")
+        if self.real_dist and self.real_dist_type not in Engine.REAL_DIST_VARIANTS:
+            raise NotImplementedError("real_dist_type %r (LSC) is outside the CUDA hot path" % (self.real_dist_type,))
+        if self.real_dist and self.real_dist_type == "noq" and not self.manhattan_spatial_dist:
+            raise NotImplementedError("SlicRealDistNoQ with manhattan_spatial_dist=False is outside the CUDA hot path")
         if self.preemptive:
             raise NotImplementedError("preemptive=True is outside the CUDA hot path")
         if not self.manhattan_spatial_dist:
@@ -210,6 +212,8 @@ class SlicModel(object):
         H, W, _ = image.shape
         params = Engine.params(compactness, min_size_factor, subsample_stride, self.convert_to_lab, max_iter,
                                collect_timing=1)
+        if self.real_dist:
+            return self._iterate_real_dist(image, params)
         clusters = np.ascontiguousarray(self._clusters)[None]
         # the lock covers the timing read-out too: it belongs to this call, not to another thread's next one
         with _locked(lambda: get_engine(H, W, self._num_components, 1, self.device)) as eng:
@@ -230,6 +234,28 @@ class SlicModel(object):
         ]))
         self.last_recorder_report = b'{"snapshots":[]}'
         return labels[0]
+
+
+def _iterate_real_dist(self, image, params):
+    """cfast_slic.pyx:198-252: the float-distance contexts, through fslic_b200_iterate_real (device buffers)."""
+    H, W, _ = image.shape
+    with _locked(lambda: get_engine(H, W, self._num_components, 1, self.device)) as eng:
+        with torch.cuda.device(eng.device):
+            img = torch.from_numpy(image).to(eng.device)[None]
+            cl = torch.from_numpy(np.ascontiguousarray(self._clusters).view(np.uint8).reshape(1, -1, 32).copy()).to(eng.device)
+            labels = eng.iterate_real(self.real_dist_type, img, cl, params)
+            ms = eng.stage_ms()
+            self._clusters = cl[0].cpu().numpy().view(CLUSTER_DTYPE).reshape(-1)
+            out = labels[0].cpu().numpy()
+    self.last_timing_report = json.dumps({
+        "name": "iterate", "duration": int(ms["iterate"] * 1000),
+        "children": [{"name": n, "duration": int(ms[n] * 1000), "children": []}
+                     for n in ("cielab_conversion", "assign", "update", "full_assign", "enforce_connectivity")]})
+    self.last_recorder_report = b'{"snapshots":[]}'
+    return out
+
+
+SlicModel._iterate_real_dist = _iterate_real_dist
 
 
 class NodeConnectivity(object):
@@ -417,6 +443,33 @@ class Slic(BaseSlic):
 
 
 SlicCuda = Slic
+
+
+class SlicRealDist(BaseSlic):
+    """== fast_slic.base_slic.SlicRealDist (base_slic.py:64-72): float distances, float spatial term."""
+    arch_name = ARCH_NAME
+    real_dist_type = "standard"
+
+    def make_slic_model(self, num_components):
+        model = SlicModel(num_components, self.arch_name)
+        model.real_dist = True
+        model.real_dist_type = self.real_dist_type
+        return model
+
+
+class SlicRealDistL2(SlicRealDist):
+    """== fast_slic.base_slic.SlicRealDistL2 (base_slic.py:74-76)."""
+    real_dist_type = "l2"
+
+
+class SlicRealDistNoQ(SlicRealDist):
+    """== fast_slic.base_slic.SlicRealDistNoQ (base_slic.py:78-85): float centroids, no quantisation."""
+    real_dist_type = "noq"
+
+    def __init__(self, *args, **kwargs):
+        float_color = kwargs.pop("float_color", True)
+        super(SlicRealDistNoQ, self).__init__(*args, **kwargs)
+        self._slic_model.float_color = float_color
 
 
 def enforce_connectivity(assignments, min_threshold, device=0):

@@ -29,6 +29,7 @@ struct PrepParams {
     int first;     // 1: re-seed colours, no update to finalise
     int finalize;  // 1: fold `acc` into the clusters
     int last;      // 1: after the final update: set is_active / is_updatable like the reference leaves them
+    int noq;       // 1: ContextRealDistNoQ -- centroids are float quotients, not rounded integers (context.cpp:375-381)
 };
 
 __global__ void __launch_bounds__(1024) k_prepare(PrepParams pp, fslic_cluster* __restrict__ clusters,
@@ -56,7 +57,14 @@ __global__ void __launch_bounds__(1024) k_prepare(PrepParams pp, fslic_cluster* 
             const unsigned long long w0 = ac[k * 4 + 0], w1 = ac[k * 4 + 1], w2 = ac[k * 4 + 2];
             const uint32_t n = (uint32_t)w0;
             c.num_members = n;  // written even when n == 0 (context.cpp:360-362)
-            if (n > 0) {
+            if (n > 0 && pp.noq) {  // (float)sum / n: int -> float conversion, IEEE division
+                const float fn = __int2float_rn((int32_t)n);
+                c.y = __fdiv_rn(__int2float_rn((int32_t)(w0 >> 32)), fn);
+                c.x = __fdiv_rn(__int2float_rn((int32_t)(uint32_t)w1), fn);
+                c.r = __fdiv_rn(__int2float_rn((int32_t)(w1 >> 32)), fn);
+                c.g = __fdiv_rn(__int2float_rn((int32_t)(uint32_t)w2), fn);
+                c.b = __fdiv_rn(__int2float_rn((int32_t)(w2 >> 32)), fn);
+            } else if (n > 0) {
                 const int32_t in = (int32_t)n, half = in / 2;
                 c.y = (float)(((int32_t)(w0 >> 32) + half) / in);
                 c.x = (float)(((int32_t)(uint32_t)w1 + half) / in);
@@ -180,7 +188,14 @@ __global__ void __launch_bounds__(256) k_prepare2(PrepParams pp, fslic_cluster* 
             const unsigned long long w0 = ac[k * 4 + 0], w1 = ac[k * 4 + 1], w2 = ac[k * 4 + 2];
             const uint32_t n = (uint32_t)w0;
             c.num_members = n;  // written even when n == 0 (context.cpp:360-362)
-            if (n > 0) {
+            if (n > 0 && pp.noq) {  // (float)sum / n: int -> float conversion, IEEE division
+                const float fn = __int2float_rn((int32_t)n);
+                c.y = __fdiv_rn(__int2float_rn((int32_t)(w0 >> 32)), fn);
+                c.x = __fdiv_rn(__int2float_rn((int32_t)(uint32_t)w1), fn);
+                c.r = __fdiv_rn(__int2float_rn((int32_t)(w1 >> 32)), fn);
+                c.g = __fdiv_rn(__int2float_rn((int32_t)(uint32_t)w2), fn);
+                c.b = __fdiv_rn(__int2float_rn((int32_t)(w2 >> 32)), fn);
+            } else if (n > 0) {
                 const int32_t in = (int32_t)n, half = in / 2;
                 c.y = (float)(((int32_t)(w0 >> 32) + half) / in);
                 c.x = (float)(((int32_t)(uint32_t)w1 + half) / in);

@@ -15,6 +15,7 @@
 #include "assign.cuh"
 #include "assign5.cuh"
 #include "graph.cuh"
+#include "realdist.cuh"
 #include "cca.cuh"
 #include "common.cuh"
 #include "lab.cuh"
@@ -652,7 +653,34 @@ static int build_patches(fslic_ctx* c, int stride, bool need_sub, float coef, cu
 }
 
 static int run_assign_pass(fslic_ctx* c, int batch, int stride, int rem, int cfg_stride, int fresh_from, bool update,
-                           float coef, cudaStream_t st, int* launches) {
+                           float coef, cudaStream_t st, int* launches, int variant = -1,
+                           const fslic_cluster* d_clusters = nullptr) {
+    if (variant >= 0) {  // float-distance variants (realdist.cuh): one thread per pixel over the cell grid
+        AssignParams ap;
+        memset(&ap, 0, sizeof(ap));
+        ap.H = c->H; ap.W = c->W; ap.K = c->K; ap.S = c->S; ap.B = batch;
+        ap.stride = stride; ap.rem = rem;
+        ap.nsub = (c->H - rem + stride - 1) / stride;
+        if (ap.nsub <= 0) return FSLIC_OK;
+        ap.cfg_stride = cfg_stride; ap.fresh_from = fresh_from;
+        ap.G = c->G; ap.cellW = c->cellW; ap.cellH = c->cellH; ap.ncell = c->ncell;
+        ap.coef = coef;
+        const long px = (long)ap.nsub * c->W * batch;
+        long grid = (px + 255) / 256;
+        if (grid > (long)c->num_sms * 32) grid = (long)c->num_sms * 32;
+        const fslic_cluster* cl = d_clusters;
+#define REAL_LAUNCH(V)                                                                                             \
+    if (update)                                                                                                    \
+        k_assign_real<V, true><<<(int)grid, 256, 0, st>>>(ap, SL_QUAD(c), SL_LABELS(c), SL_CINFO(c), SL_CELLS(c), cl, SL_ACC(c)); \
+    else                                                                                                           \
+        k_assign_real<V, false><<<(int)grid, 256, 0, st>>>(ap, SL_QUAD(c), SL_LABELS(c), SL_CINFO(c), SL_CELLS(c), cl, SL_ACC(c));
+        if (variant == 0) { REAL_LAUNCH(0) } else if (variant == 1) { REAL_LAUNCH(1) } else { REAL_LAUNCH(2) }
+#undef REAL_LAUNCH
+        c->last_assign_impl = 0;
+        if (launches) *launches += 1;
+        CK(cudaGetLastError());
+        return FSLIC_OK;
+    }
     const PassGeom g = pass_geometry(c, stride);
     AssignParams ap;
     ap.H = c->H; ap.W = c->W; ap.K = c->K; ap.S = c->S; ap.B = batch;
@@ -796,11 +824,11 @@ static int run_assign_pass(fslic_ctx* c, int batch, int stride, int rem, int cfg
 }
 
 static int run_prepare(fslic_ctx* c, fslic_cluster* d_clusters, int batch, int first, int finalize, cudaStream_t st,
-                       int* launches) {
+                       int* launches, int noq = 0) {
     PrepParams pp;
     pp.H = c->H; pp.W = c->W; pp.K = c->K; pp.S = c->S; pp.T = 2 * c->S + 32;
     pp.G = c->G; pp.cellW = c->cellW; pp.cellH = c->cellH; pp.ncell = c->ncell;
-    pp.first = first; pp.finalize = finalize; pp.last = 0;
+    pp.first = first; pp.finalize = finalize; pp.last = 0; pp.noq = noq;
     const size_t smem = (size_t)(c->ncell + 2) * sizeof(int);
     // k_prepare2 (one thread per cluster, several CTAs per image) is quicker for a handful of images (single image:
     // 0.412 vs 0.431 ms per blocking call); with a full batch its extra CTAs only contend (18 vs 13 us at 32 images)
@@ -839,7 +867,7 @@ static int check_params(const fslic_ctx* c, const fslic_params* p, float* coef_o
 // `batch` images starting at image `b0` of the context's buffers.  Leaves the pre-CCA labels in c->labels.
 static int iterate_front(fslic_ctx* c, int b0, const uint8_t* d_images, fslic_cluster* d_clusters, int batch,
                          const fslic_params* p, float coef, cudaStream_t st, int* launches, bool timing,
-                         bool lab_done = false) {
+                         bool lab_done = false, int variant = -1) {
     c->slice = b0;
     int rc = FSLIC_OK;
     if (!lab_done) rc = launch_lab(c, d_images, SL_QUAD(c), batch, p->convert_to_lab, st);  // else: the caller ran it
@@ -847,20 +875,25 @@ static int iterate_front(fslic_ctx* c, int b0, const uint8_t* d_images, fslic_cl
     (*launches)++;
     if (timing) CK(cudaEventRecord(c->ev[1], st));
     const int stride = p->subsample_stride;
-    rc = build_patches(c, stride, p->max_iter > 0, coef, st, launches);
-    if (rc) return rc;
+    const int noq = variant == 2 ? 1 : 0;
+    if (variant < 0) {
+        rc = build_patches(c, stride, p->max_iter > 0, coef, st, launches);
+        if (rc) return rc;
+    }
+    const fslic_cluster* cl = d_clusters;  // the NoQ variant reads its float centroids from the cluster records themselves
     int rem = 0;
     for (int it = 0; it < p->max_iter; it++) {
-        rc = run_prepare(c, d_clusters, batch, it == 0, it > 0, st, launches);
+        rc = run_prepare(c, d_clusters, batch, it == 0, it > 0, st, launches, noq);
         if (rc) return rc;
-        rc = run_assign_pass(c, batch, stride, rem, stride, it, true, coef, st, launches);
+        rc = run_assign_pass(c, batch, stride, rem, stride, it, true, coef, st, launches, variant, cl);
         if (rc) return rc;
         rem = (rem + 1) % stride;
     }
     if (timing) CK(cudaEventRecord(c->ev[2], st));
-    rc = run_prepare(c, d_clusters, batch, p->max_iter == 0, p->max_iter > 0, st, launches);
+    rc = run_prepare(c, d_clusters, batch, p->max_iter == 0, p->max_iter > 0, st, launches, noq);
     if (rc) return rc;
-    rc = run_assign_pass(c, batch, 1, 0, stride, p->max_iter < stride ? p->max_iter : stride, false, coef, st, launches);
+    rc = run_assign_pass(c, batch, 1, 0, stride, p->max_iter < stride ? p->max_iter : stride, false, coef, st, launches,
+                         variant, cl);
     c->slice = 0;
     return rc;
 }
@@ -876,7 +909,7 @@ static int iterate_graphed(fslic_ctx* c, const uint8_t* d_images, fslic_cluster*
                            const fslic_params* p, cudaStream_t st);
 
 static int iterate_plain(fslic_ctx* c, const uint8_t* d_images, fslic_cluster* d_clusters, uint16_t* d_labels,
-                         int batch, const fslic_params* p, void* stream, bool lab_done = false) {
+                         int batch, const fslic_params* p, void* stream, bool lab_done = false, int variant = -1) {
     int rc = check_batch(c, batch);
     if (rc) return rc;
     float coef;
@@ -891,7 +924,7 @@ static int iterate_plain(fslic_ctx* c, const uint8_t* d_images, fslic_cluster* d
     c->cca_timing = timing;
     c->cca_timed = false;
     if (timing) CK(cudaEventRecord(c->ev[0], st));
-    rc = iterate_front(c, 0, d_images, d_clusters, batch, p, coef, st, &launches, timing, lab_done);
+    rc = iterate_front(c, 0, d_images, d_clusters, batch, p, coef, st, &launches, timing, lab_done, variant);
     if (rc) return rc;
     if (timing) CK(cudaEventRecord(c->ev[3], st));
     rc = iterate_back(c, d_labels, batch, p, st, &launches);
@@ -945,6 +978,14 @@ extern "C" int fslic_b200_iterate(fslic_ctx* c, const uint8_t* d_images, fslic_c
         if (have || again) return iterate_graphed(c, d_images, d_clusters, d_labels, batch, p, (cudaStream_t)stream);
     }
     return iterate_plain(c, d_images, d_clusters, d_labels, batch, p, stream);
+}
+
+// The float-distance contexts of the reference (context.h:100-125; cfast_slic.pyx:198-252): variant 0 = ContextRealDist
+// ("standard"), 1 = ContextRealDistL2, 2 = ContextRealDistNoQ with manhattan_spatial_dist (its default).
+extern "C" int fslic_b200_iterate_real(fslic_ctx* c, int variant, const uint8_t* d_images, fslic_cluster* d_clusters,
+                                       uint16_t* d_labels, int batch, const fslic_params* p, void* stream) {
+    if (variant < 0 || variant > 2) return set_err(FSLIC_EINVAL, "variant must be 0 (standard), 1 (l2) or 2 (noq)");
+    return iterate_plain(c, d_images, d_clusters, d_labels, batch, p, stream, false, variant);
 }
 
 extern "C" int fslic_b200_assign_kernel_time(fslic_ctx* c, float* total_ms, int* launches) {

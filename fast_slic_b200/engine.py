@@ -102,6 +102,20 @@ class Engine:
                                              C.byref(params), _stream_ptr(self.device)))
         return labels
 
+    REAL_DIST_VARIANTS = {"standard": 0, "l2": 1, "noq": 2}
+
+    def iterate_real(self, variant, images, clusters, params, labels=None):
+        """Float-distance variants (fslic_b200_iterate_real): variant "standard" | "l2" | "noq"; device tensors."""
+        self._check_images(images)
+        B = images.shape[0]
+        if labels is None:
+            labels = torch.empty((B, self.H, self.W), dtype=torch.int16, device=self.device)
+        with self.lock:
+            check(self._L.fslic_b200_iterate_real(self._h, self.REAL_DIST_VARIANTS[variant], images.data_ptr(),
+                                                  clusters.data_ptr(), labels.data_ptr(), B, C.byref(params),
+                                                  _stream_ptr(self.device)))
+        return labels
+
     def enforce_connectivity(self, labels, K, min_threshold):
         """In place on int16/uint16 labels [B,H,W] (cuda)."""
         B = labels.shape[0]

@@ -89,6 +89,15 @@ int fslic_b200_initialize_clusters(fslic_ctx* ctx, const uint8_t* d_images, fsli
 int fslic_b200_iterate(fslic_ctx* ctx, const uint8_t* d_images, fslic_cluster* d_clusters, uint16_t* d_labels,
                        int batch, const fslic_params* params, void* stream);
 
+/* == the float-distance contexts ContextRealDist / ContextRealDistL2 / ContextRealDistNoQ (context.h:100-125,
+ *    context.cpp:394-499; selected in cfast_slic.pyx:198-252 by SlicModel.real_dist_type): `variant` 0 = "standard"
+ *    (the default kernel with float distances and an untruncated float spatial term), 1 = "l2" (squared colour and
+ *    spatial distances), 2 = "noq" (float centroids, no quantisation in the update; Manhattan spatial term, the
+ *    reference's default).  Same buffers and semantics as fslic_b200_iterate; results bit-identical to the reference
+ *    (every float operation in its order and rounding). */
+int fslic_b200_iterate_real(fslic_ctx* ctx, int variant, const uint8_t* d_images, fslic_cluster* d_clusters,
+                            uint16_t* d_labels, int batch, const fslic_params* params, void* stream);
+
 /* The same call as the reference-facing plugin makes it: HOST buffers in, HOST buffers out
  * (what SlicModel.iterate does with a numpy image, cfast_slic.pyx:150-260).  H2D copy, kernels and
  * D2H copy are pipelined over chunks of 32 images on three streams (pass pinned buffers for true overlap);

@@ -141,6 +141,18 @@ class Port:
         self.lib.orc_cluster_density_to_mask(H, W, K, _p(labels, _u16p), _p(densities, _u8p), _p(out, _u8p))
         return out
 
+    def iterate_real(self, variant, image, clusters, max_iter=10, compactness=10.0, min_size_factor=0.25, stride=3,
+                     convert_to_lab=True, stages=False):
+        """Float-distance contexts (context.cpp:394-499): variant 0 standard, 1 l2, 2 noq."""
+        image = np.ascontiguousarray(image)
+        H, W, _ = image.shape
+        out = np.zeros((H, W), np.uint16)
+        pre = np.zeros((H, W), np.uint16)
+        self.lib.orc_iterate_real(int(variant), H, W, len(clusters), _p(image, _u8p), clusters.ctypes.data_as(C.c_void_p),
+                                  _p(out, _u16p), max_iter, C.c_float(compactness), C.c_float(min_size_factor), stride,
+                                  int(convert_to_lab), _p(pre, _u16p))
+        return (out, pre) if stages else out
+
 
 class Ref:
     """The unmodified reference (standard or x64/avx2 arch), OpenMP threads = num_threads (-1: all)."""
@@ -209,3 +221,14 @@ class Ref:
         self.lib.ref_cluster_density_to_mask(H, W, K, clusters.ctypes.data_as(C.c_void_p), _p(labels, _u16p),
                                              _p(densities, _u8p), _p(out, _u8p))
         return out
+
+    def iterate_real(self, variant, image, clusters, max_iter=10, compactness=10.0, min_size_factor=0.25, stride=3,
+                     convert_to_lab=True, stages=False, num_threads=2):
+        image = np.ascontiguousarray(image)
+        H, W, _ = image.shape
+        out = np.zeros((H, W), np.uint16)
+        pre = np.zeros((H, W), np.uint16)
+        self.lib.ref_iterate_real(int(variant), H, W, len(clusters), _p(image, _u8p), clusters.ctypes.data_as(C.c_void_p),
+                                  _p(out, _u16p), max_iter, C.c_float(compactness), C.c_float(min_size_factor), stride,
+                                  int(convert_to_lab), num_threads, _p(pre, _u16p))
+        return (out, pre) if stages else out

@@ -53,6 +53,25 @@ void configure(Ctx& ctx, float compactness, float min_size_factor, int stride, i
     ctx.manhattan_spatial_dist = true;
     ctx.debug_mode = false;
 }
+// float-distance contexts (context.h:100-125), driven like cfast_slic.pyx:198-252: variant 0 = ContextRealDist
+// ("standard"), 1 = ContextRealDistL2, 2 = ContextRealDistNoQ
+template <typename Base>
+struct ProbeReal : public Base {
+    ProbeReal(int H, int W, int K, const uint8_t* image, Cluster* clusters) : Base(H, W, K, image, clusters) {}
+    void dump(uint16_t* precca_out) {
+        if (!precca_out) return;
+        for (int i = 0; i < this->H; i++)
+            for (int j = 0; j < this->W; j++) precca_out[i * this->W + j] = this->assignment.get(i, j);
+    }
+};
+template <typename Ctx>
+void run_real(Ctx& ctx, uint16_t* out, int max_iter, float compactness, float min_size_factor, int stride, int convert_to_lab,
+              int num_threads, uint16_t* precca_out) {
+    configure(ctx, compactness, min_size_factor, stride, convert_to_lab, num_threads);
+    ctx.initialize_state();
+    ctx.iterate(out, max_iter);
+    ctx.dump(precca_out);
+}
 }  // namespace
 
 extern "C" {
@@ -92,6 +111,22 @@ void ref_enforce_connectivity(uint16_t* labels, int H, int W, int K, int min_thr
     fsparallel::Scope scope(num_threads);
     cca::ConnectivityEnforcer ce(labels, H, W, K, min_threshold);
     ce.execute(labels);
+}
+
+// float-distance contexts, cfast_slic.pyx:198-252: variant 0 = ContextRealDist, 1 = ContextRealDistL2, 2 = ContextRealDistNoQ
+void ref_iterate_real(int variant, int H, int W, int K, const uint8_t* image, Cluster* clusters, uint16_t* out, int max_iter,
+                      float compactness, float min_size_factor, int stride, int convert_to_lab, int num_threads,
+                      uint16_t* precca_out) {
+    if (variant == 0) {
+        ProbeReal<fslic::ContextRealDist> ctx(H, W, K, image, clusters);
+        run_real(ctx, out, max_iter, compactness, min_size_factor, stride, convert_to_lab, num_threads, precca_out);
+    } else if (variant == 1) {
+        ProbeReal<fslic::ContextRealDistL2> ctx(H, W, K, image, clusters);
+        run_real(ctx, out, max_iter, compactness, min_size_factor, stride, convert_to_lab, num_threads, precca_out);
+    } else {
+        ProbeReal<fslic::ContextRealDistNoQ> ctx(H, W, K, image, clusters);
+        run_real(ctx, out, max_iter, compactness, min_size_factor, stride, convert_to_lab, num_threads, precca_out);
+    }
 }
 
 // fast-slic.cpp:16-78 through the door cfast_slic.pyx:262-270 uses.  counts[K], neighbors[K * 12] (max_conn = 12).

@@ -544,3 +544,153 @@ void orc_get_mask_density(int H, int W, int K, const OrcCluster* clusters, const
 void orc_cluster_density_to_mask(int H, int W, int K, const uint16_t* assignment, const uint8_t* densities, uint8_t* result) {
     for (long p = 0; p < (long)H * W; p++) result[p] = assignment[p] < (uint16_t)K ? densities[assignment[p]] : 0;
 }
+
+/* ------------------------------------------------------------------ */
+/* float-distance variants: src/context.cpp:394-499, context.h:100-125  */
+/*   variant 0  ContextRealDist      BaseContext<float>: the default kernel with float min_dists and an         */
+/*              UNtruncated float spatial patch  patch = coef * (|di| + |dj|)  (context.cpp:23-33, :259-298)      */
+/*   variant 1  ContextRealDistL2    squared colour distance + patch = dj*dj + di*di, di = coef*(i-S) -- the      */
+/*              reference's object code fuses it as fma(dj, dj, round(di*di)) (context.cpp:394-445)              */
+/*   variant 2  ContextRealDistNoQ   float centroids, no window truncation to int16, per-pixel                   */
+/*              |dr|+|dg|+|db|+|dx|+|dy| summed left to right, float division in the update (:447-499, :375-381)  */
+/* Same scheduler, same strict '>' against min_dists (first visitor wins ties), same integer sums in update().    */
+/* ------------------------------------------------------------------ */
+static void assign_pass_real(int variant, int H, int W, int K, int S, OrcCluster* clusters, const uint8_t* quad, float coef,
+                             uint16_t* assignment, float* min_dists, int stride, int rem) {
+    for (long p = 0; p < (long)H * W; p++) min_dists[p] = 3.402823466e+38f; /* numeric_limits<float>::max(), :201-206 */
+    for (int k = 0; k < K; k++) {
+        float x = clusters[k].x, y = clusters[k].y;
+        clusters[k].x = x < 0 ? 0 : (x > (float)(W - 1) ? (float)(W - 1) : x);
+        clusters[k].y = y < 0 ? 0 : (y > (float)(H - 1) ? (float)(H - 1) : y);
+    }
+    int T = 2 * S + 32;
+    int cell_W = ceil_int(W, T), cell_H = ceil_int(H, T);
+    int ncell = cell_W * cell_H;
+    int* start = (int*)calloc((size_t)ncell + 1, sizeof(int));
+    int* items = (int*)malloc(sizeof(int) * (size_t)(K > 0 ? K : 1));
+    for (int k = 0; k < K; k++) {
+        if (!clusters[k].is_active) continue;
+        start[cell_W * ((int)clusters[k].y / T) + ((int)clusters[k].x / T) + 1]++;
+    }
+    for (int c = 0; c < ncell; c++) start[c + 1] += start[c];
+    int* fill = (int*)malloc(sizeof(int) * (size_t)(ncell > 0 ? ncell : 1));
+    memcpy(fill, start, sizeof(int) * (size_t)ncell);
+    for (int k = 0; k < K; k++) {
+        if (!clusters[k].is_active) continue;
+        items[fill[cell_W * ((int)clusters[k].y / T) + ((int)clusters[k].x / T)]++] = k;
+    }
+    for (int phase = 0; phase < 4; phase++)
+        for (int ci = phase / 2; ci < cell_H; ci += 2)
+            for (int cj = phase % 2; cj < cell_W; cj += 2) {
+                int cell = ci * cell_W + cj;
+                for (int t = start[cell]; t < start[cell + 1]; t++) {
+                    int k = items[t];
+                    const OrcCluster* c = &clusters[k];
+                    int i0, i1, j0, j1;
+                    int16_t cy = (int16_t)c->y, cx = (int16_t)c->x;
+                    int16_t cr = (int16_t)c->r, cg = (int16_t)c->g, cb = (int16_t)c->b;
+                    if (variant == 2) { /* :472-473: float arithmetic, truncated by my_max<int> / my_min<int> */
+                        i0 = (int)(c->y - (float)S); if (i0 < 0) i0 = 0;
+                        i1 = (int)(c->y + (float)S + 1.0f); if (i1 > H) i1 = H;
+                        j0 = (int)(c->x - (float)S); if (j0 < 0) j0 = 0;
+                        j1 = (int)(c->x + (float)S + 1.0f); if (j1 > W) j1 = W;
+                        i1--; j1--;
+                    } else {
+                        i0 = cy - S < 0 ? 0 : cy - S; i1 = cy + S >= H ? H - 1 : cy + S;
+                        j0 = cx - S < 0 ? 0 : cx - S; j1 = cx + S >= W ? W - 1 : cx + S;
+                    }
+                    for (int i = i0; i <= i1; i++) {
+                        if (i % stride != rem) continue;
+                        for (int j = j0; j <= j1; j++) {
+                            long p = (long)i * W + j;
+                            int r = quad[4 * p], g = quad[4 * p + 1], b = quad[4 * p + 2];
+                            float d;
+                            if (variant == 0) {
+                                float patch = coef * (float)(abs(i - cy) + abs(j - cx));
+                                d = patch + (float)(abs(r - cr) + abs(g - cg) + abs(b - cb));
+                            } else if (variant == 1) {
+                                float di = coef * (float)(i - cy), dj = coef * (float)(j - cx);
+                                float patch = fmaf(dj, dj, di * di);
+                                float dr = (float)(r - cr), dg = (float)(g - cg), db = (float)(b - cb);
+                                d = patch + (dr * dr + dg * dg + db * db); /* integers below 2^24: exact in any order */
+                            } else {
+                                float dr = (float)r - c->r, dg = (float)g - c->g, db = (float)b - c->b;
+                                float dy = coef * ((float)i - c->y), dx = coef * ((float)j - c->x);
+                                d = fabsf(dr) + fabsf(dg) + fabsf(db) + fabsf(dx) + fabsf(dy);
+                            }
+                            if (min_dists[p] > d) {
+                                min_dists[p] = d;
+                                assignment[p] = c->number;
+                            }
+                        }
+                    }
+                }
+            }
+    free(start); free(items); free(fill);
+}
+
+static void update_pass_real(int variant, int H, int W, int K, OrcCluster* clusters, const uint8_t* quad,
+                             const uint16_t* assignment, int stride, int rem) {
+    if (variant != 2) {
+        update_pass(H, W, K, clusters, quad, assignment, stride, rem);
+        return;
+    }
+    int32_t* n = (int32_t*)calloc((size_t)K, sizeof(int32_t));
+    int32_t* acc = (int32_t*)calloc((size_t)K * 5, sizeof(int32_t));
+    for (int i = rem; i < H; i += stride)
+        for (int j = 0; j < W; j++) {
+            long p = (long)i * W + j;
+            uint16_t c = assignment[p];
+            if (c == 0xFFFF) continue;
+            n[c]++;
+            acc[5 * c + 0] += i; acc[5 * c + 1] += j;
+            acc[5 * c + 2] += quad[4 * p]; acc[5 * c + 3] += quad[4 * p + 1]; acc[5 * c + 4] += quad[4 * p + 2];
+        }
+    for (int k = 0; k < K; k++) {
+        OrcCluster* c = &clusters[k];
+        if (!c->is_updatable) continue;
+        c->num_members = (uint32_t)n[k];
+        if (n[k] == 0) continue;
+        c->y = (float)acc[5 * k + 0] / (float)n[k]; /* :375-381: (float)sum / int -> float division */
+        c->x = (float)acc[5 * k + 1] / (float)n[k];
+        c->r = (float)acc[5 * k + 2] / (float)n[k];
+        c->g = (float)acc[5 * k + 3] / (float)n[k];
+        c->b = (float)acc[5 * k + 4] / (float)n[k];
+    }
+    free(n); free(acc);
+}
+
+void orc_iterate_real(int variant, int H, int W, int K, const uint8_t* image, OrcCluster* clusters, uint16_t* out, int max_iter,
+                      float compactness, float min_size_factor, int stride, int convert_to_lab, uint16_t* precca_out) {
+    if (H <= 0 || W <= 0 || K <= 0) return;
+    int S = (int16_t)sqrt((double)(H * W / K));
+    long N = (long)H * W;
+    uint8_t* quad = (uint8_t*)malloc((size_t)N * 4);
+    uint16_t* assignment = (uint16_t*)malloc(sizeof(uint16_t) * (size_t)N);
+    float* min_dists = (float*)malloc(sizeof(float) * (size_t)N);
+    int color_shift = convert_to_lab ? OUTPUT_SHIFT : 0;
+    orc_rgb_to_quad(image, H, W, convert_to_lab, quad);
+    for (int k = 0; k < K; k++) {
+        int y = clampi((int)clusters[k].y, 0, H - 1), x = clampi((int)clusters[k].x, 0, W - 1);
+        clusters[k].r = quad[4 * ((long)y * W + x)];
+        clusters[k].g = quad[4 * ((long)y * W + x) + 1];
+        clusters[k].b = quad[4 * ((long)y * W + x) + 2];
+    }
+    for (long p = 0; p < N; p++) assignment[p] = 0xFFFF;
+    float coef = 1.0f / ((float)S / compactness);
+    coef *= (float)(1 << color_shift);
+    for (int k = 0; k < K; k++) clusters[k].is_updatable = 2;
+    int rem = 0;
+    for (int it = 0; it < max_iter; it++) {
+        assign_pass_real(variant, H, W, K, S, clusters, quad, coef, assignment, min_dists, stride, rem);
+        update_pass_real(variant, H, W, K, clusters, quad, assignment, stride, rem);
+        rem = (rem + 1) % stride;
+    }
+    for (int k = 0; k < K; k++) clusters[k].is_active = 1;
+    assign_pass_real(variant, H, W, K, S, clusters, quad, coef, assignment, min_dists, 1, 0);
+    if (precca_out) memcpy(precca_out, assignment, sizeof(uint16_t) * (size_t)N);
+    memcpy(out, assignment, sizeof(uint16_t) * (size_t)N);
+    int thres = (int)round((double)(S * S) * (double)min_size_factor);
+    orc_enforce_connectivity(out, H, W, K, thres);
+    free(quad); free(assignment); free(min_dists);
+}

@@ -60,6 +60,11 @@ class Checker:
         return self._impl.iterate(image, clusters, max_iter, compactness, min_size_factor, stride, convert_to_lab,
                                   stages=stages)
 
+    def iterate_real(self, variant, image, clusters, max_iter=10, compactness=10.0, min_size_factor=0.25, stride=3,
+                     convert_to_lab=True, stages=False):
+        return self._impl.iterate_real(variant, image, clusters, max_iter, compactness, min_size_factor, stride,
+                                       convert_to_lab, stages=stages)
+
     def get_connectivity(self, labels, K):
         return self._impl.get_connectivity(labels, K)
 

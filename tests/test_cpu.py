@@ -331,3 +331,21 @@ def test_cython_stub_builds_and_binds(tmp_path):
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError):
             model.initialize(np.zeros((48, 64, 3), np.uint8))
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_oracle_real_dist_variants_match_compiled_reference(port, ref, variant):
+    """ContextRealDist / ContextRealDistL2 / ContextRealDistNoQ (context.cpp:394-499): the restatement's float
+    arithmetic (one multiply + one add; fma(dj, dj, di*di); left-to-right |.| sums and float quotients) reproduces the
+    compiled reference bit for bit -- pre-CCA labels, final labels, Cluster bytes."""
+    for kind, H, W, K, kw in [("syn", 120, 160, 48, {}), ("noise", 97, 131, 37, dict(min_size_factor=0.0)),
+                              ("syn", 240, 320, 150, dict(compactness=30.0)), ("blocks", 200, 300, 150, {}),
+                              ("syn", 150, 200, 30, dict(subsample_stride=2, max_iter=3)), ("flat", 97, 131, 37, {}),
+                              ("syn", 180, 240, 70, dict(convert_to_lab=False))]:
+        sigma, a = split_kwargs(kw)
+        img = make_image(kind, H, W, seed=31, sigma=sigma)
+        c1, c2 = port.initialize(img, K), ref.initialize(img, K)
+        args = (a["max_iter"], a["compactness"], a["min_size_factor"], a["subsample_stride"], a["convert_to_lab"])
+        o1, p1 = port.iterate_real(variant, img, c1, *args, stages=True)
+        o2, p2 = ref.iterate_real(variant, img, c2, *args, stages=True)
+        assert (p1 == p2).all() and (o1 == o2).all() and c1.tobytes() == c2.tobytes(), (variant, kind, H, W, K)

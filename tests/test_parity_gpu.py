@@ -484,3 +484,36 @@ def test_cython_stub_parity(checker, tmp_path):
         assert got.dtype == np.int16 and (got.view(np.uint16) == want).all()
         for k, c in enumerate(model.clusters):
             assert c["number"] == k and c["yx"] == (float(cl[k]["y"]), float(cl[k]["x"])) and c["num_members"] == int(cl[k]["num_members"])
+
+
+REAL_CASES = [("syn", 120, 160, 48, {}), ("noise", 97, 131, 37, dict(min_size_factor=0.0)),
+              ("syn", 240, 320, 150, dict(compactness=30.0)), ("blocks", 200, 300, 150, {}),
+              ("syn", 150, 200, 30, dict(subsample_stride=2, max_iter=3)), ("flat", 97, 131, 37, {}),
+              ("syn", 180, 240, 70, dict(convert_to_lab=False)), ("syn", 480, 640, 200, dict(min_size_factor=0.1)),
+              ("thin", 10, 400, 5, {})]
+
+
+@pytest.mark.parametrize("variant", ["standard", "l2", "noq"])
+@pytest.mark.parametrize("case", REAL_CASES, ids=lambda c: "%s_%dx%d_K%d" % c[:4])
+def test_real_dist_variants(checker, variant, case):
+    """SlicRealDist / SlicRealDistL2 / SlicRealDistNoQ (fast_slic/base_slic.py:64-85 -> context.cpp:394-499) on the GPU:
+    float distances, every operation in the reference's order and rounding -- labels and raw Cluster bytes (float
+    centroids of the NoQ variant included) identical to the compiled reference, cold start and warm start."""
+    import fast_slic_b200 as fs
+    kind, H, W, K, kw = case
+    kind = "syn" if kind == "thin" else kind
+    sigma, args = split_kwargs(kw)
+    img = make_image(kind, H, W, seed=41, sigma=sigma)
+    cls = {"standard": fs.SlicRealDist, "l2": fs.SlicRealDistL2, "noq": fs.SlicRealDistNoQ}[variant]
+    s = cls(num_components=K, compactness=args["compactness"], min_size_factor=args["min_size_factor"],
+            subsample_stride=args["subsample_stride"], convert_to_lab=args["convert_to_lab"])
+    v = {"standard": 0, "l2": 1, "noq": 2}[variant]
+    cl = checker.initialize(img, K)
+    for round_ in range(2):
+        got = s.iterate(img, args["max_iter"]).view(np.uint16)
+        want = checker.iterate_real(v, img, cl, args["max_iter"], args["compactness"], args["min_size_factor"],
+                                    args["subsample_stride"], args["convert_to_lab"])
+        assert (got == want).all(), "%s round %d: %d px differ" % (variant, round_, int((got != want).sum()))
+        gc = s.slic_model.cluster_array
+        for f in ("y", "x", "r", "g", "b", "num_members", "number", "is_active", "is_updatable"):
+            assert (gc[f] == cl[f]).all(), "%s round %d: cluster field %s" % (variant, round_, f)
