@@ -155,6 +155,157 @@ __global__ void __launch_bounds__(1024) k_prepare(PrepParams pp, fslic_cluster* 
 }
 
 // ---------------------------------------------------------------------------------------------
+// k_prepare3: k_prepare for K <= 4096 with the latency taken out (round 2).  k_prepare goes to global memory four
+// times in a row per cluster (load record, store the unsorted CInfo, load it back after the scan, store it sorted) and
+// handles its two clusters per thread one after the other.  Here every thread loads all its clusters up front, keeps
+// the CInfo records in registers, and the shared-memory atomicAdd that counts a cell also hands out the record's rank
+// inside the cell -- so after ONE scan the records go straight to their sorted slots: one global load round trip, one
+// store, four barriers.  Same results (order inside a cell is arbitrary for both; consumers rank by sort key).
+// ---------------------------------------------------------------------------------------------
+#define PREP3_PER 4  // clusters per thread at most (K <= 4096 with 1024 threads)
+__global__ void __launch_bounds__(1024) k_prepare3(PrepParams pp, fslic_cluster* __restrict__ clusters,
+                                                   unsigned long long* __restrict__ acc, const uint32_t* __restrict__ quad,
+                                                   CInfo* __restrict__ cinfo, int* __restrict__ cell_start) {
+    extern __shared__ int s_cnt[];  // ncell + 1 counters
+    __shared__ int s_warp[32];
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    fslic_cluster* cl = clusters + (size_t)b * pp.K;
+    unsigned long long* ac = acc + (size_t)b * pp.K * 4;
+    const uint32_t* qd = quad + (size_t)b * pp.H * pp.W;
+    CInfo* ci_sorted = cinfo + (size_t)b * pp.K;
+    int* cs = cell_start + (size_t)b * (pp.ncell + 1);
+    const int ncnt = pp.ncell + 1;
+    for (int c = tid; c < ncnt; c += nt) s_cnt[c] = 0;
+
+    // all global loads of this thread's clusters in flight together
+    uint4 ca[PREP3_PER], cb[PREP3_PER];
+    ulonglong2 a01[PREP3_PER];
+    unsigned long long a2[PREP3_PER];
+#pragma unroll
+    for (int u = 0; u < PREP3_PER; u++) {
+        const int k = tid + u * nt;
+        if (k < pp.K) {
+            const uint4* p = reinterpret_cast<const uint4*>(cl + k);
+            ca[u] = p[0];
+            cb[u] = p[1];
+            if (pp.finalize) {
+                a01[u] = *reinterpret_cast<const ulonglong2*>(ac + (size_t)k * 4);
+                a2[u] = ac[(size_t)k * 4 + 2];
+            }
+        }
+    }
+    __syncthreads();  // histogram zeroed
+    CInfo rec[PREP3_PER];
+    int cell[PREP3_PER], rank[PREP3_PER];
+#pragma unroll
+    for (int u = 0; u < PREP3_PER; u++) {
+        const int k = tid + u * nt;
+        cell[u] = -1;
+        if (k < pp.K) {
+            fslic_cluster c;
+            memcpy(&c, &ca[u], 16);
+            memcpy(reinterpret_cast<char*>(&c) + 16, &cb[u], 16);
+            if (pp.finalize) {
+                // packed sums: [0] = n | sum_y << 32, [1] = sum_x | sum_L << 32, [2] = sum_a | sum_b << 32
+                const unsigned long long w0 = a01[u].x, w1 = a01[u].y, w2 = a2[u];
+                const uint32_t n = (uint32_t)w0;
+                c.num_members = n;  // written even when n == 0 (context.cpp:360-362)
+                if (n > 0 && pp.noq) {
+                    const float fn = __int2float_rn((int32_t)n);
+                    c.y = __fdiv_rn(__int2float_rn((int32_t)(w0 >> 32)), fn);
+                    c.x = __fdiv_rn(__int2float_rn((int32_t)(uint32_t)w1), fn);
+                    c.r = __fdiv_rn(__int2float_rn((int32_t)(w1 >> 32)), fn);
+                    c.g = __fdiv_rn(__int2float_rn((int32_t)(uint32_t)w2), fn);
+                    c.b = __fdiv_rn(__int2float_rn((int32_t)(w2 >> 32)), fn);
+                } else if (n > 0) {
+                    const int32_t in = (int32_t)n, half = in / 2;
+                    c.y = (float)(((int32_t)(w0 >> 32) + half) / in);
+                    c.x = (float)(((int32_t)(uint32_t)w1 + half) / in);
+                    c.r = (float)(((int32_t)(w1 >> 32) + half) / in);
+                    c.g = (float)(((int32_t)(uint32_t)w2 + half) / in);
+                    c.b = (float)(((int32_t)(w2 >> 32) + half) / in);
+                }
+                *reinterpret_cast<ulonglong2*>(ac + (size_t)k * 4) = make_ulonglong2(0ull, 0ull);
+                ac[(size_t)k * 4 + 2] = 0ull;
+            }
+            if (pp.first) {
+                int y = min(max((int)c.y, 0), pp.H - 1), x = min(max((int)c.x, 0), pp.W - 1);
+                const uint32_t q = qd[(size_t)y * pp.W + x];
+                c.r = (float)(q & 0xff);
+                c.g = (float)((q >> 8) & 0xff);
+                c.b = (float)((q >> 16) & 0xff);
+            }
+            // safeguard clamp, stored back like the reference does
+            c.x = fminf(fmaxf(c.x, 0.f), (float)(pp.W - 1));
+            c.y = fminf(fmaxf(c.y, 0.f), (float)(pp.H - 1));
+            c.number = (uint16_t)k;
+            c.is_active = 1;
+            c.is_updatable = 2;
+            uint4 o0, o1;
+            memcpy(&o0, &c, 16);
+            memcpy(&o1, reinterpret_cast<char*>(&c) + 16, 16);
+            uint4* p = reinterpret_cast<uint4*>(cl + k);
+            p[0] = o0;
+            p[1] = o1;
+
+            const int cy = (int16_t)c.y, cx = (int16_t)c.x;
+            const int cr = (int16_t)c.r, cg = (int16_t)c.g, cbl = (int16_t)c.b;
+            const int phase = 2 * ((cy / pp.T) & 1) + ((cx / pp.T) & 1);
+            rec[u].cyx = (cy & 0xffff) | (cx << 16);
+            rec[u].color = (uint32_t)(cr & 0xff) | ((uint32_t)(cg & 0xff) << 8) | ((uint32_t)(cbl & 0xff) << 16);
+            rec[u].sortkey = ((uint32_t)phase << 16) | (uint32_t)k;
+            rec[u].pad = 0;
+            cell[u] = (cy / pp.G) * pp.cellW + (cx / pp.G);
+            rank[u] = atomicAdd(&s_cnt[cell[u]], 1);  // count the cell and take a slot inside it
+        }
+    }
+    __syncthreads();
+    {   // exclusive scan of the cell histogram: every thread owns a run of consecutive cells
+        const int per = (ncnt + nt - 1) / nt;
+        const int c0 = tid * per;
+        int local = 0;
+        for (int u = 0; u < per; u++) {
+            const int c = c0 + u;
+            if (c < ncnt) local += s_cnt[c];
+        }
+        int x = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int y = __shfl_up_sync(FSLIC_FULL, x, o);
+            if ((tid & 31) >= o) x += y;
+        }
+        if ((tid & 31) == 31) s_warp[tid >> 5] = x;
+        __syncthreads();
+        if (tid < 32) {
+            int w = (tid < (nt >> 5)) ? s_warp[tid] : 0;
+            int z = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int y = __shfl_up_sync(FSLIC_FULL, z, o);
+                if (tid >= o) z += y;
+            }
+            s_warp[tid] = z - w;
+        }
+        __syncthreads();
+        int run = s_warp[tid >> 5] + x - local;
+        for (int u = 0; u < per; u++) {
+            const int c = c0 + u;
+            if (c < ncnt) {
+                const int v = s_cnt[c];
+                s_cnt[c] = run;
+                cs[c] = run;
+                run += v;
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < PREP3_PER; u++)
+        if (cell[u] >= 0) ci_sorted[s_cnt[cell[u]] + rank[u]] = rec[u];
+}
+
+// ---------------------------------------------------------------------------------------------
 // k_prepare2: the same bookkeeping spread over ceil(K / 256) CTAs per image (round 2).  k_prepare is one CTA per image
 // and latency bound -- two clusters per thread one after the other, five block barriers -- 13 us per launch, eleven
 // launches per iterate: a third of a single image's device time.  Here every cluster has its own thread (steps 1-3 of

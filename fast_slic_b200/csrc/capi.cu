@@ -317,6 +317,7 @@ static int create_impl(int device, int H, int W, int K, int max_batch, bool cca_
     CKC(cudaFuncSetAttribute(k_debug_heap_select, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin - 4 * 1024));
     CKC(cudaFuncSetAttribute(k_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
     CKC(cudaFuncSetAttribute(k_prepare2, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+    CKC(cudaFuncSetAttribute(k_prepare3, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
     CKC(cudaFuncSetAttribute(k_rgb_to_lab16, cudaFuncAttributeMaxDynamicSharedMemorySize, LAB16_SMEM));
     *out = c;
     return FSLIC_OK;
@@ -834,7 +835,9 @@ static int run_prepare(fslic_ctx* c, fslic_cluster* d_clusters, int batch, int f
     // 0.412 vs 0.431 ms per blocking call); with a full batch its extra CTAs only contend (18 vs 13 us at 32 images)
     static const int forced = getenv("FSLIC_PREPARE") ? atoi(getenv("FSLIC_PREPARE")) : 0;
     const bool old_prepare = forced == 1 || (forced != 2 && batch >= 8);
-    if (old_prepare)
+    if (forced != 1 && forced != 2 && c->K <= 1024 * PREP3_PER)
+        k_prepare3<<<batch, 1024, smem, st>>>(pp, d_clusters, SL_ACC(c), SL_QUAD(c), SL_CINFO(c), SL_CELLS(c));
+    else if (old_prepare)
         k_prepare<<<batch, 1024, smem, st>>>(pp, d_clusters, SL_ACC(c), SL_QUAD(c), SL_CINFO(c), SL_CELLS(c),
                                              c->cinfo_tmp + (size_t)c->slice * c->K);
     else
