@@ -499,6 +499,9 @@ def main():
         k_ms += a
         k_n += n
     stage = eng.stage_ms()
+    cca_stage = eng.cca_stage_ms()
+    kernel_name = ("k_assign5<TS,3,true,TPS> (TMA-staged fused assign+update, subsampled pass)" if eng.assign_impl() == 5
+                   else "k_assign_warp<TS,3,true> (fused assign+update, subsampled pass)")
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     if os.path.exists(peaks_path):
@@ -516,10 +519,10 @@ def main():
         traffic = tj.get("%s_batch%d" % (args.workload, B), {}).get("traffic")
     except Exception:
         pass
-    roofline = {"kernel": "k_assign_warp<TS,3,true> (fused assign+update, subsampled pass)", "bound": "hbm",
+    roofline = {"kernel": kernel_name, "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "bytes_per_launch": alg_bytes, "avg_launch_us": avg_ms * 1e3,
-                "launches_timed": k_n, "stage_ms_last_step": stage}
+                "launches_timed": k_n, "stage_ms_last_step": stage, "cca_stage_ms_last_step": cca_stage}
 
     # ---- end to end through the public API with HOST buffers (H2D + compute + D2H inside the timed region) ----
     slic = Slic(num_components=K, compactness=COMPACTNESS, min_size_factor=msf, subsample_stride=STRIDE)

@@ -103,6 +103,7 @@ struct fslic_ctx {
     uint16_t* d_lab = nullptr;
     cudaStream_t own_stream = nullptr, in_stream = nullptr, out_stream = nullptr, side_stream = nullptr;
     cudaEvent_t side_fork = nullptr, side_join = nullptr, tail_done = nullptr;
+    long long* selprof = nullptr;       // FSLIC_SELPROF=1: 8 words per image written by k_cca_select (diagnostics)
     CcaCounters* h_counters = nullptr;  // pinned, 64 entries: lets the host path learn which images need the replay
     std::vector<cudaEvent_t> pipe_ev;  // [2 * chunks]: input-ready / compute-done events of iterate_host
     // timing
@@ -198,6 +199,7 @@ extern "C" int fslic_b200_destroy(fslic_ctx* c) {
     if (c->tail_done) cudaEventDestroy(c->tail_done);
     if (c->gexec) cudaGraphExecDestroy(c->gexec);
     if (c->h_counters) cudaFreeHost(c->h_counters);
+    if (c->selprof) cudaFree(c->selprof);
     for (auto& e : c->pipe_ev) cudaEventDestroy(e);
     delete c;
     return FSLIC_OK;
@@ -300,6 +302,12 @@ static int create_impl(int device, int H, int W, int K, int max_batch, bool cca_
     CKC(cudaEventCreateWithFlags(&c->side_join, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&c->tail_done, cudaEventDisableTiming));
     CKC(cudaMallocHost(reinterpret_cast<void**>(&c->h_counters), 64 * sizeof(CcaCounters)));
+    if (const char* e = getenv("FSLIC_SELPROF")) {
+        if (atoi(e) != 0) {
+            CKC(cudaMalloc(reinterpret_cast<void**>(&c->selprof), (size_t)c->cca_batch * 8 * sizeof(long long)));
+            CKC(cudaMemset(c->selprof, 0, (size_t)c->cca_batch * 8 * sizeof(long long)));
+        }
+    }
 
     // opt in to large dynamic shared memory once
     for (int ts : {128, 192, 256, 384})
@@ -484,7 +492,7 @@ static int run_cca(fslic_ctx* c, const uint16_t* d_in, uint16_t* d_out, int batc
             int rc2 = copy_runs(0);
             if (rc2) return rc2;
         }
-        k_cca_select<<<nb, 1024, SEL_CHUNK * 8 + (cp.heap_in_smem ? heap_bytes : 0), st>>>(cp, c->carea, c->counters, c->heap);
+        k_cca_select<<<nb, 1024, SEL_CHUNK * 8 + (cp.heap_in_smem ? heap_bytes : 0), st>>>(cp, c->carea, c->counters, c->heap, c->selprof);
         tail(split ? 1 : -1, st);
         if (early) {
             CK(cudaEventRecord(c->tail_done, st));
@@ -1003,6 +1011,15 @@ extern "C" int fslic_b200_debug_cca_counters(fslic_ctx* c, int32_t* out8, int im
     USE_DEVICE(c->device);
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(out8, c->counters + image, sizeof(CcaCounters), cudaMemcpyDeviceToHost));
+    return FSLIC_OK;
+}
+
+extern "C" int fslic_b200_debug_select_profile(fslic_ctx* c, long long* out8, int image) {
+    if (!c || !out8 || image < 0 || image >= c->cca_batch) return set_err(FSLIC_EINVAL, "bad argument");
+    if (!c->selprof) return set_err(FSLIC_EINVAL, "the context was created without FSLIC_SELPROF=1");
+    USE_DEVICE(c->device);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out8, c->selprof + 8 * image, 8 * sizeof(long long), cudaMemcpyDeviceToHost));
     return FSLIC_OK;
 }
 

@@ -658,13 +658,117 @@ __device__ __forceinline__ void hs_adjust_heap(const HeapMem<SMEM>& h, int hole,
     h.put(hole + 1, value);
 }
 
+// The __heap_select loop over the queued candidates (cca.cpp:226) on ONE warp with the heap in shared memory, padded
+// with +infinity slots up to 2K+3 so that a node's children can always be loaded: missing children compare as
+// +infinity, which reproduces libstdc++'s one-child and leaf cases without any bounds test.
+//
+// It is a PIPELINE of sift-downs.  Each __pop_heap only ever writes the node it currently stands on and moves down one
+// level per half-step, so the next one may start at the root as soon as its predecessor stands on level >= 2: it then
+// reads / writes strictly above everything the predecessor can still touch.  One trip of the loop = two half-steps of
+// every sift-down in flight (a lane holds at most one: shared address of its hole and of the hole's children, its
+// value) + at most one new sift-down.
+//
+// The loop is a single dependent chain on an in-order warp, i.e. its speed is the sum of the issue stalls of its
+// instructions (first version: 85 instructions, 298 clocks per trip).  Hence PTX, and a selection step without
+// cross-lane traffic other than one vote: the next 32 queue elements sit in registers, one per lane (`alive` = not yet
+// consumed); elements in front of the first one that beats the root can be dropped for good (the root only grows); the
+// lane HOLDING the first hit starts its sift-down itself (no find-first-set, no shuffles).  If that lane is still busy
+// with an earlier sift-down (possible right after a window reload) the hit simply stays where it is and is retried in
+// the next trip -- the root has not changed, and a sift-down ends within `depth` half-steps.
+#define SEL_HALF_STEP                                                                                       \
+    "ld.volatile.shared.v4.u32 {a0, a1, b0, b1}, [c];\n\t"                                                  \
+    "setp.gt.u32 tl, b1, a1;\n\t"            /* right child unless area[right] > area[left] */             \
+    "min.u32 chi, a1, b1;\n\t"                                                                            \
+    "selp.b32 clo, a0, b0, tl;\n\t"                                                                       \
+    "setp.le.and.u32 mv, chi, vhi, act;\n\t" /* the child moves up, the hole moves down */                 \
+    "min.u32 ohi, chi, vhi;\n\t"                                                                          \
+    "selp.b32 olo, clo, vlo, mv;\n\t"                                                                     \
+    "@act st.volatile.shared.v2.u32 [hole], {olo, ohi};\n\t" /* ... or the value lands here */             \
+    "add.u32 c8, c, 8;\n\t"                                                                               \
+    "selp.b32 nh, c, c8, tl;\n\t"                                                                         \
+    "selp.b32 hole, nh, rooth, mv;\n\t"      /* idle lanes rest on the root: their loads are one broadcast */ \
+    "add.u32 t0, hole, hole;\n\t"                                                                         \
+    "sub.u32 c, t0, base;\n\t"               /* slot(h) = h + 1; children at slots 2h+2, 2h+3 */           \
+    "mov.pred act, mv;\n\t"
+
+__device__ __forceinline__ int sel_replay_smem(uint32_t heap_saddr, uint32_t queue_saddr, int qn, int consumed, int depth, int lane,
+                                               long long& trips_out) {
+    uint32_t cnt = 0, trips = 0;
+    if (consumed < qn) {
+        // No bar.warp.sync between the half-steps: the loop has no divergent branch (everything is predicated, the two
+        // branches test vote results), the shared accesses are volatile (never reordered), and a warp's shared-memory
+        // instructions execute in issue order; vote.sync reconverges the warp once per trip anyway.
+        asm volatile(
+            "{\n\t"
+            ".reg .pred act, mv, tl, p, some, first, nact, take, kill, inq;\n\t"
+            ".reg .b32 base, c, hole, vlo, vhi, a0, a1, b0, b1, chi, clo, ohi, olo, c8, nh, t0, t1, t2, root, hit, elo, ehi;\n\t"
+            ".reg .b32 lt, le, wpos, idx, qaddr, rooth, drain;\n\t"
+            "mov.u32 base, %2;\n\t"
+            "mov.u32 lt, %%lanemask_lt;\n\t"
+            "mov.u32 le, %%lanemask_le;\n\t"
+            "add.u32 rooth, base, 8;\n\t"     // root = slot 1, its children = slots 2, 3
+            "mov.u32 hole, rooth;\n\t"
+            "add.u32 c, base, 16;\n\t"
+            "mov.u32 vlo, 0;\n\t"
+            "mov.u32 vhi, 0;\n\t"
+            "setp.ne.u32 act, 0, 0;\n\t"
+            "mov.u32 wpos, %5;\n\t"
+            "SEL_LOAD:\n\t"                    // the window [wpos, wpos + 32) of the queue, one element per lane
+            "add.u32 idx, wpos, %6;\n\t"
+            "setp.lt.s32 inq, idx, %4;\n\t"
+            "mov.u32 elo, 0;\n\t"
+            "mov.u32 ehi, 0;\n\t"              // area 0 never beats the root: consumed / missing elements
+            "shl.b32 qaddr, idx, 3;\n\t"
+            "add.u32 qaddr, qaddr, %3;\n\t"
+            "@inq ld.shared.v2.u32 {elo, ehi}, [qaddr];\n\t"
+            "SEL_TRIP:\n\t"
+            "add.u32 %1, %1, 1;\n\t"
+            SEL_HALF_STEP
+            "ld.volatile.shared.u32 root, [base+12];\n\t"  // final: the newest sift-down has left level 0
+            SEL_HALF_STEP
+            "setp.gt.u32 p, ehi, root;\n\t"    // comp(i, first) of __heap_select
+            "vote.sync.ballot.b32 hit, p, 0xffffffff;\n\t"
+            "vote.sync.any.pred some, p, 0xffffffff;\n\t"
+            "@!some bra.uni SEL_NEXT;\n\t"
+            "and.b32 t1, hit, lt;\n\t"
+            "setp.eq.and.u32 first, t1, 0, p;\n\t"
+            "not.pred nact, act;\n\t"
+            "and.pred take, first, nact;\n\t"
+            "and.b32 t2, hit, le;\n\t"
+            "setp.eq.or.u32 kill, t2, 0, take;\n\t"  // elements in front of the first hit are gone for good
+            "@take mov.u32 vlo, elo;\n\t"
+            "@take mov.u32 vhi, ehi;\n\t"
+            "@take add.u32 %0, %0, 1;\n\t"
+            "@kill mov.u32 ehi, 0;\n\t"
+            "or.pred act, act, take;\n\t"
+            "bra.uni SEL_TRIP;\n\t"
+            "SEL_NEXT:\n\t"                    // nothing left in the window beats the root, and the root only grows
+            "add.u32 wpos, wpos, 32;\n\t"
+            "setp.lt.s32 inq, wpos, %4;\n\t"
+            "@inq bra.uni SEL_LOAD;\n\t"
+            "mov.u32 drain, %7;\n\t"           // no sift-down takes more than `depth` half-steps
+            "SEL_DRAIN:\n\t"
+            SEL_HALF_STEP
+            "sub.u32 drain, drain, 1;\n\t"
+            "setp.gt.s32 inq, drain, 0;\n\t"
+            "@inq bra.uni SEL_DRAIN;\n\t"
+            "}\n\t"
+            : "+r"(cnt), "+r"(trips)
+            : "r"(heap_saddr), "r"(queue_saddr), "r"(qn), "r"(consumed), "r"(lane), "r"(depth)
+            : "memory");
+        __syncwarp();
+    }
+    trips_out = trips;
+    return (int)__reduce_add_sync(FSLIC_FULL, cnt);
+}
+
 // generic body shared by the pipeline kernel and the debug entry point
 template <bool SMEM>
 __device__ __forceinline__ void heap_select_body(const uint32_t* __restrict__ area, int ncomp, int K, int thres,
                                                   const HeapMem<SMEM> heap, uint32_t* __restrict__ mark_out /* |= 1<<31 */,
                                                   uint8_t* __restrict__ kept_bytes /* or nullptr */,
                                                   unsigned long long* s_queue /* shared, SEL_CHUNK entries */,
-                                                  int* dbg_ops = nullptr) {
+                                                  int* dbg_ops = nullptr, long long* prof = nullptr /* 8 words, diagnostics */) {
     __shared__ int s_warp[32];
     __shared__ int s_qn, s_filled;
     __shared__ uint32_t s_min;
@@ -676,6 +780,7 @@ __device__ __forceinline__ void heap_select_body(const uint32_t* __restrict__ ar
     if (SMEM)  // +infinity padding behind the K live slots (see the replay loop)
         for (int u = K + 1 + tid; u < 2 * K + 4; u += nt) heap.put(u, 0u, 0xffffffffu);
     __syncthreads();
+    long long pt_filter = 0, pt_build = 0, pt_replay = 0, pn_iter = 0, pn_queue = 0, pn_chunks = 0, pt0 = clock64(), pt_mark = pt0;
     // thread t owns components base + t*SEL_PER .. +SEL_PER-1 (ascending order inside the thread); the next
     // chunk is prefetched into registers while warp 0 replays the current one
     uint32_t cur[SEL_PER], nxt[SEL_PER];
@@ -729,6 +834,13 @@ __device__ __forceinline__ void heap_select_body(const uint32_t* __restrict__ ar
         }
         __syncthreads();
         const int qn = s_qn;
+        if (prof && tid == 0) {
+            const long long now = clock64();
+            pt_filter += now - pt_mark;
+            pt_mark = now;
+            pn_queue += qn;
+            pn_chunks++;
+        }
         // phase 1: the first K candidates fill the heap array in order
         int consumed = 0;
         if (filling) {
@@ -749,6 +861,11 @@ __device__ __forceinline__ void heap_select_body(const uint32_t* __restrict__ ar
                 __syncthreads();
             }
         }
+        if (prof && tid == 0) {
+            const long long now = clock64();
+            pt_build += now - pt_mark;
+            pt_mark = now;
+        }
         if (f == K && warp == 0) {
             // phase 2: the rest of the queue in order (cca.cpp:226 -> __heap_select loop), as a PIPELINE of
             // sift-downs inside one warp.  Each __pop_heap only ever writes the node it currently stands on
@@ -760,62 +877,9 @@ __device__ __forceinline__ void heap_select_body(const uint32_t* __restrict__ ar
             // levels behind its predecessor), and `depth` half-steps after the last issue everything is done.
             int nops = 0;
             if (SMEM) {
-                // Shared-memory heap, padded with +infinity slots up to 2K+3 so a node's children can always be
-                // loaded: missing children compare as +infinity, which reproduces libstdc++'s one-child and
-                // leaf cases without any bounds test.  State per lane: shared byte address of its hole.
-                bool act = false;
-                uint32_t haddr = heap.s + 8u, vlo = 0, vhi = 0;
-                int qpos = consumed, next_lane = 0;
-                const int depth = 32 - __clz(K);
-                const uint32_t q_saddr = (uint32_t)__cvta_generic_to_shared(s_queue);
-                const uint32_t base = heap.s;
-                auto level_step = [&]() {
-                    const uint32_t caddr = 2u * haddr - base;  // slot(h) = h + 1 ; children at slots 2h+2, 2h+3
-                    uint32_t c0lo = 0, c0hi = 0, c1lo = 0, c1hi = 0;
-                    if (act) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                                          : "=r"(c0lo), "=r"(c0hi), "=r"(c1lo), "=r"(c1hi) : "r"(caddr));
-                    const bool tl = c1hi > c0hi;  // right unless area[right] > area[left]
-                    const uint32_t clo = tl ? c0lo : c1lo, chi = tl ? c0hi : c1hi;
-                    const bool mv = act && !(chi > vhi);
-                    if (act) asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(haddr), "r"(mv ? clo : vlo), "r"(mv ? chi : vhi) : "memory");
-                    haddr = mv ? (tl ? caddr : caddr + 8u) : haddr;
-                    act = mv;
-                    __syncwarp();
-                };
-                // main loop: one (attempted) issue per iteration.  Fast path: the very next queue element beats the
-                // root (the common case: the filter already removed most that cannot); otherwise every lane looks
-                // at one element of the window [qpos, qpos+32) and whole windows are skipped at once -- elements
-                // that do not beat the root now never will, the root only grows.
-                while (qpos < qn) {
-                    level_step();
-                    uint32_t elo = 0, ehi = 0, root_area;
-                    if (qpos + lane < qn)
-                        asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(elo), "=r"(ehi) : "r"(q_saddr + 8u * (uint32_t)(qpos + lane)));
-                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(root_area) : "r"(base + 12u));
-                    level_step();
-                    const unsigned hit = __ballot_sync(FSLIC_FULL, ehi > root_area);  // lanes past qn hold ehi = 0
-                    if (hit == 0) {
-                        qpos += 32;
-                    } else {
-                        const int first = __ffs(hit) - 1;  // comp(i, first): __pop_heap(first, middle, i)
-                        const uint32_t ilo = __shfl_sync(FSLIC_FULL, elo, first);
-                        const uint32_t ihi = __shfl_sync(FSLIC_FULL, ehi, first);
-                        if (lane == next_lane) {
-                            act = true;
-                            haddr = base + 8u;
-                            vlo = ilo;
-                            vhi = ihi;
-                        }
-                        next_lane = (next_lane + 1) & 31;
-                        nops++;
-                        qpos += first + 1;
-                    }
-                }
-                // drain: no sift-down takes more than `depth` levels
-                for (int d = 0; d < depth; d += 2) {
-                    level_step();
-                    level_step();
-                }
+                long long trips = 0;
+                nops = sel_replay_smem(heap.s, (uint32_t)__cvta_generic_to_shared(s_queue), qn, consumed, 32 - __clz(K), lane, trips);
+                pn_iter += trips;
             } else {
             bool act = false;
             int hole = 0;
@@ -870,12 +934,27 @@ __device__ __forceinline__ void heap_select_body(const uint32_t* __restrict__ ar
             if (lane == 0) {
                 s_min = hs_area(heap.get(1));
                 if (dbg_ops) *dbg_ops += nops;
+                if (prof) {
+                    const long long now = clock64();
+                    pt_replay += now - pt_mark;
+                    pt_mark = now;
+                }
             }
         }
         if (tid == 0) s_filled = f;
         __syncthreads();
 #pragma unroll
         for (int u = 0; u < SEL_PER; u++) cur[u] = nxt[u];
+    }
+    if (prof && tid == 0) {
+        prof[0] = clock64() - pt0;
+        prof[1] = pt_filter;
+        prof[2] = pt_build;
+        prof[3] = pt_replay;
+        prof[4] = pn_iter;
+        prof[5] = pn_queue;
+        prof[6] = pn_chunks;
+        prof[7] = ncomp;
     }
     // publish the selected set
     const int filled = s_filled;
@@ -888,23 +967,24 @@ __device__ __forceinline__ void heap_select_body(const uint32_t* __restrict__ ar
 
 __global__ void __launch_bounds__(1024) k_cca_select(CcaParams cp, uint32_t* __restrict__ carea_all,
                                                      CcaCounters* __restrict__ counters,
-                                                     unsigned long long* __restrict__ heap_global) {
+                                                     unsigned long long* __restrict__ heap_global, long long* __restrict__ prof_all) {
     extern __shared__ __align__(16) unsigned char sel_smem[];  // [queue: SEL_CHUNK x u64][heap: (2K+4) x u64 if it fits]
     unsigned long long* s_queue = reinterpret_cast<unsigned long long*>(sel_smem);
     const int b = blockIdx.x;
     CcaCounters* ct = &counters[b];
     if (!ct->need_sim) return;  // k_cca_threshold settled it (or cca.cpp:225 is not taken)
     uint32_t* area = carea_all + (size_t)b * cp.N;
+    long long* prof = prof_all ? prof_all + 8 * b : nullptr;
     if (cp.heap_in_smem) {
         HeapMem<true> hm;
         hm.g = nullptr;
         hm.s = (uint32_t)__cvta_generic_to_shared(sel_smem + SEL_CHUNK * 8);
-        heap_select_body<true>(area, ct->ncomp, cp.K, cp.thres, hm, area, nullptr, s_queue, &ct->dbg_ops);
+        heap_select_body<true>(area, ct->ncomp, cp.K, cp.thres, hm, area, nullptr, s_queue, &ct->dbg_ops, prof);
     } else {
         HeapMem<false> hm;
         hm.g = heap_global + (size_t)b * ((cp.K + 3) & ~1);
         hm.s = 0;
-        heap_select_body<false>(area, ct->ncomp, cp.K, cp.thres, hm, area, nullptr, s_queue, &ct->dbg_ops);
+        heap_select_body<false>(area, ct->ncomp, cp.K, cp.thres, hm, area, nullptr, s_queue, &ct->dbg_ops, prof);
     }
     if (threadIdx.x == 0) ct->sel_mode = 1;
 }

@@ -159,6 +159,11 @@ int fslic_b200_assign_kernel_time(fslic_ctx* ctx, float* total_ms, int* launches
  * ncomp, ncand, nkept, sel_mode, keep_thres, need_sim, heap_ops, kth_area. */
 int fslic_b200_debug_cca_counters(fslic_ctx* ctx, int32_t* out8, int image);
 
+/* Diagnostics (contexts created with FSLIC_SELPROF=1 in the environment): 8 int64 words written by the
+ * std::partial_sort replay of image `image`: total / filter / heap build / replay clocks, replay loop trips,
+ * queued candidates, chunks, components. */
+int fslic_b200_debug_select_profile(fslic_ctx* ctx, long long* out8, int image);
+
 /* Milliseconds spent per stage in the last iterate() with collect_timing != 0. */
 int fslic_b200_stage_ms(fslic_ctx* ctx, float* out_ms, int count);
 
