@@ -675,8 +675,8 @@ __device__ __forceinline__ void hs_adjust_heap(const HeapMem<SMEM>& h, int hole,
 // lane HOLDING the first hit starts its sift-down itself (no find-first-set, no shuffles).  If that lane is still busy
 // with an earlier sift-down (possible right after a window reload) the hit simply stays where it is and is retried in
 // the next trip -- the root has not changed, and a sift-down ends within `depth` half-steps.
+#define SEL_CHILDREN "ld.volatile.shared.v4.u32 {a0, a1, b0, b1}, [c];\n\t"
 #define SEL_HALF_STEP                                                                                       \
-    "ld.volatile.shared.v4.u32 {a0, a1, b0, b1}, [c];\n\t"                                                  \
     "setp.gt.u32 tl, b1, a1;\n\t"            /* right child unless area[right] > area[left] */             \
     "min.u32 chi, a1, b1;\n\t"                                                                            \
     "selp.b32 clo, a0, b0, tl;\n\t"                                                                       \
@@ -713,6 +713,7 @@ __device__ __forceinline__ int sel_replay_smem(uint32_t heap_saddr, uint32_t que
             "mov.u32 vhi, 0;\n\t"
             "setp.ne.u32 act, 0, 0;\n\t"
             "mov.u32 wpos, %5;\n\t"
+            SEL_CHILDREN
             "SEL_LOAD:\n\t"                    // the window [wpos, wpos + 32) of the queue, one element per lane
             "add.u32 idx, wpos, %6;\n\t"
             "setp.lt.s32 inq, idx, %4;\n\t"
@@ -723,12 +724,15 @@ __device__ __forceinline__ int sel_replay_smem(uint32_t heap_saddr, uint32_t que
             "@inq ld.shared.v2.u32 {elo, ehi}, [qaddr];\n\t"
             "SEL_TRIP:\n\t"
             "add.u32 %1, %1, 1;\n\t"
-            SEL_HALF_STEP
+            SEL_HALF_STEP                      // (its children were loaded at the end of the previous trip)
             "ld.volatile.shared.u32 root, [base+12];\n\t"  // final: the newest sift-down has left level 0
+            SEL_CHILDREN
             SEL_HALF_STEP
             "setp.gt.u32 p, ehi, root;\n\t"    // comp(i, first) of __heap_select
             "vote.sync.ballot.b32 hit, p, 0xffffffff;\n\t"
             "vote.sync.any.pred some, p, 0xffffffff;\n\t"
+            SEL_CHILDREN                       // of the next trip's first half-step: a lane that starts a sift-down now was
+                                               // resting on the root, so the addresses do not depend on the decision below
             "@!some bra.uni SEL_NEXT;\n\t"
             "and.b32 t1, hit, lt;\n\t"
             "setp.eq.and.u32 first, t1, 0, p;\n\t"
@@ -749,6 +753,7 @@ __device__ __forceinline__ int sel_replay_smem(uint32_t heap_saddr, uint32_t que
             "mov.u32 drain, %7;\n\t"           // no sift-down takes more than `depth` half-steps
             "SEL_DRAIN:\n\t"
             SEL_HALF_STEP
+            SEL_CHILDREN
             "sub.u32 drain, drain, 1;\n\t"
             "setp.gt.s32 inq, drain, 0;\n\t"
             "@inq bra.uni SEL_DRAIN;\n\t"
