@@ -306,6 +306,121 @@ __global__ void __launch_bounds__(1024) k_prepare3(PrepParams pp, fslic_cluster*
 }
 
 // ---------------------------------------------------------------------------------------------
+// prepare_in_tail: the finalize / record / counting-sort work of k_prepare3 (no colour re-seed) as a device function
+// for the TAIL of an assign+update launch: the last CTA of k_assign5 to finish (ticket counter) calls it, so that a
+// single image's ten passes do not pay a kernel boundary between "update" and "next assign" (the eleven k_prepare
+// launches were a third of a single image's device time).  The caller's registers are capped at 64 per thread, so the
+// records wait in shared memory instead of registers: `smem` needs prepare_tail_smem_bytes(K, ncell) bytes.  The
+// accumulators were written by RED.64 from other SMs: they are read with ld.global.cg (L2).  K <= 4096.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ size_t prepare_tail_smem_bytes(int K, int ncell) {
+    return (size_t)((ncell + 1 + 3) & ~3) * 4 + 32 * 4 + (size_t)K * 16 + (size_t)K * 4;
+}
+
+__device__ __forceinline__ void prepare_in_tail(const PrepParams& pp, fslic_cluster* __restrict__ cl,
+                                                unsigned long long* __restrict__ ac, CInfo* __restrict__ ci_sorted,
+                                                int* __restrict__ cs, unsigned char* smem, int tid, int nt) {
+    const int ncnt = pp.ncell + 1;
+    int* s_cnt = reinterpret_cast<int*>(smem);
+    int* s_warp = s_cnt + ((ncnt + 3) & ~3);
+    uint4* s_rec = reinterpret_cast<uint4*>(s_warp + 32);
+    int* s_slot = reinterpret_cast<int*>(s_rec + pp.K);  // cell << 12 | rank inside the cell
+    for (int c = tid; c < ncnt; c += nt) s_cnt[c] = 0;
+    __syncthreads();
+    for (int k = tid; k < pp.K; k += nt) {
+        uint4* gp = reinterpret_cast<uint4*>(cl + k);
+        const uint4 g0 = gp[0], g1 = gp[1];
+        fslic_cluster c;
+        memcpy(&c, &g0, 16);
+        memcpy(reinterpret_cast<char*>(&c) + 16, &g1, 16);
+        {
+            const uint4 a01 = __ldcg(reinterpret_cast<const uint4*>(ac + (size_t)k * 4));
+            const uint2 a2 = __ldcg(reinterpret_cast<const uint2*>(ac + (size_t)k * 4 + 2));
+            // packed sums: [0] = n | sum_y << 32, [1] = sum_x | sum_L << 32, [2] = sum_a | sum_b << 32
+            const uint32_t n = a01.x;
+            c.num_members = n;  // written even when n == 0 (context.cpp:360-362)
+            if (n > 0) {
+                const int32_t in = (int32_t)n, half = in / 2;
+                c.y = (float)(((int32_t)a01.y + half) / in);
+                c.x = (float)(((int32_t)a01.z + half) / in);
+                c.r = (float)(((int32_t)a01.w + half) / in);
+                c.g = (float)(((int32_t)a2.x + half) / in);
+                c.b = (float)(((int32_t)a2.y + half) / in);
+            }
+            *reinterpret_cast<ulonglong2*>(ac + (size_t)k * 4) = make_ulonglong2(0ull, 0ull);
+            ac[(size_t)k * 4 + 2] = 0ull;
+        }
+        c.x = fminf(fmaxf(c.x, 0.f), (float)(pp.W - 1));
+        c.y = fminf(fmaxf(c.y, 0.f), (float)(pp.H - 1));
+        c.number = (uint16_t)k;
+        c.is_active = 1;
+        c.is_updatable = 2;
+        uint4 o0, o1;
+        memcpy(&o0, &c, 16);
+        memcpy(&o1, reinterpret_cast<char*>(&c) + 16, 16);
+        gp[0] = o0;
+        gp[1] = o1;
+        const int cy = (int16_t)c.y, cx = (int16_t)c.x;
+        const int cr = (int16_t)c.r, cg = (int16_t)c.g, cbl = (int16_t)c.b;
+        const int phase = 2 * ((cy / pp.T) & 1) + ((cx / pp.T) & 1);
+        uint4 rec;
+        rec.x = (uint32_t)((cy & 0xffff) | (cx << 16));
+        rec.y = (uint32_t)(cr & 0xff) | ((uint32_t)(cg & 0xff) << 8) | ((uint32_t)(cbl & 0xff) << 16);
+        rec.z = ((uint32_t)phase << 16) | (uint32_t)k;
+        rec.w = 0;
+        s_rec[k] = rec;
+        const int cell = (cy / pp.G) * pp.cellW + (cx / pp.G);
+        s_slot[k] = (cell << 12) | atomicAdd(&s_cnt[cell], 1);
+    }
+    __syncthreads();
+    {   // exclusive scan of the cell histogram: every thread owns a run of consecutive cells
+        const int per = (ncnt + nt - 1) / nt;
+        const int c0 = tid * per;
+        int local = 0;
+        for (int u = 0; u < per; u++) {
+            const int c = c0 + u;
+            if (c < ncnt) local += s_cnt[c];
+        }
+        int x = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int y = __shfl_up_sync(FSLIC_FULL, x, o);
+            if ((tid & 31) >= o) x += y;
+        }
+        if ((tid & 31) == 31) s_warp[tid >> 5] = x;
+        __syncthreads();
+        if (tid < 32) {
+            int w = (tid < (nt >> 5)) ? s_warp[tid] : 0;
+            int z = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int y = __shfl_up_sync(FSLIC_FULL, z, o);
+                if (tid >= o) z += y;
+            }
+            s_warp[tid] = z - w;
+        }
+        __syncthreads();
+        int run = s_warp[tid >> 5] + x - local;
+        for (int u = 0; u < per; u++) {
+            const int c = c0 + u;
+            if (c < ncnt) {
+                const int v = s_cnt[c];
+                s_cnt[c] = run;
+                cs[c] = run;
+                run += v;
+            }
+        }
+    }
+    __syncthreads();
+    uint4* out = reinterpret_cast<uint4*>(ci_sorted);
+    for (int k = tid; k < pp.K; k += nt) {
+        const int sl = s_slot[k];
+        out[s_cnt[sl >> 12] + (sl & 4095)] = s_rec[k];
+    }
+    __syncthreads();  // the shared buffers are reused by the next image
+}
+
+// ---------------------------------------------------------------------------------------------
 // k_prepare2: the same bookkeeping spread over ceil(K / 256) CTAs per image (round 2).  k_prepare is one CTA per image
 // and latency bound -- two clusters per thread one after the other, five block barriers -- 13 us per launch, eleven
 // launches per iterate: a third of a single image's device time.  Here every cluster has its own thread (steps 1-3 of
@@ -471,6 +586,7 @@ struct AssignParams {
     int wstride, db, dty, dsx;      // a warp's step through the super tiles, decomposed into (image, tile row, column) carries
     uint32_t tbl_bytes;             // patch size in shared memory, padded to 128 bytes
     uint32_t cinfo_img_bytes, cells_img_bytes, acc_img_bytes;  // per-image pitches of cinfo / cell_start / acc
+    int fuse_prepare;               // 1: the last CTA to finish runs prepare_in_tail for the next pass (small batches)
 };
 
 #define AS_WARPS 16

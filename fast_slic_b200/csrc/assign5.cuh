@@ -126,12 +126,13 @@ __device__ __forceinline__ uint32_t a5_prmt(uint32_t a, uint32_t b, uint32_t sel
 // per-byte equality of two words whose bytes are all below 0x80 -> 0x80 in every equal byte (3 logic ops)
 __device__ __forceinline__ uint32_t eq7(uint32_t w, uint32_t m) { return ~((w ^ m) + 0x7f7f7f7fu) & 0x80808080u; }
 
-template <int TS, int STRIDE, bool UPDATE, int TPS>
+template <int TS, int STRIDE, bool UPDATE, int TPS, bool FUSE = false>
 __global__ void __launch_bounds__(32 * A5_MAXWARPS, 1)
     k_assign5(const __grid_constant__ AssignParams ap, const __grid_constant__ CUtensorMap tm_quad,
               const __grid_constant__ CUtensorMap tm_lab, const uint32_t* __restrict__ quad, uint16_t* __restrict__ labels,
               const CInfo* __restrict__ cinfo, const int* __restrict__ cell_start, unsigned long long* __restrict__ acc,
-              const uint16_t* __restrict__ g_tbl) {
+              const uint16_t* __restrict__ g_tbl, fslic_cluster* clusters, CInfo* cinfo_next, int* cell_start_next,
+              unsigned int* ticket) {
     constexpr int R = 4;                      // sub-rows per tile (one per register of a lane)
     constexpr int BW = 32 * TPS;              // columns of a super tile == TMA box width
     constexpr uint32_t QBYTES = BW * R * 4;   // bytes one quad box delivers (out-of-image parts included: zero fill)
@@ -513,4 +514,25 @@ __global__ void __launch_bounds__(32 * A5_MAXWARPS, 1)
         b = nb; ty = nty; sx = nsx;
     }
     if (store_pending && lane == 0) a5_store_wait_read();  // the staging tile must outlive the last bulk store's read
+    if (UPDATE && FUSE) {
+        // Small batches: the bookkeeping between two passes (k_prepare3's work) runs right here, in the last CTA to
+        // finish, instead of in a kernel of its own.  cinfo_next / cell_start_next alias cinfo / cell_start: they are
+        // written only after every CTA of the grid has taken its ticket, i.e. has read them for the last time.
+        __shared__ int s_last;
+        __threadfence();  // this thread's RED.64 are performed before its CTA's ticket is
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1u) ? 1 : 0;
+        __syncthreads();
+        if (s_last) {
+            if (threadIdx.x == 0) *ticket = 0u;  // zero between launches
+            __threadfence();
+            PrepParams pp;
+            pp.H = ap.H; pp.W = ap.W; pp.K = ap.K; pp.S = ap.S; pp.T = 2 * ap.S + 32;
+            pp.G = ap.G; pp.cellW = ap.cellW; pp.cellH = ap.cellH; pp.ncell = ap.ncell;
+            pp.first = 0; pp.finalize = 1; pp.last = 0; pp.noq = 0;
+            for (int bi = 0; bi < ap.B; bi++)
+                prepare_in_tail(pp, clusters + (size_t)bi * ap.K, acc + (size_t)bi * ap.K * 4, cinfo_next + (size_t)bi * ap.K,
+                                cell_start_next + (size_t)bi * (ap.ncell + 1), smem_raw, (int)threadIdx.x, (int)blockDim.x);
+        }
+    }
 }

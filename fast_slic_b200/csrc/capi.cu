@@ -27,8 +27,8 @@ typedef void (*assign_fn)(AssignParams, const uint32_t*, uint16_t*, const CInfo*
 static assign_fn pick_assign(int TS, int stride, bool update);
 
 typedef void (*assign5_fn)(const AssignParams, const CUtensorMap, const CUtensorMap, const uint32_t*, uint16_t*, const CInfo*,
-                           const int*, unsigned long long*, const uint16_t*);
-static assign5_fn pick_assign5(int TS, bool update, int tps);
+                           const int*, unsigned long long*, const uint16_t*, fslic_cluster*, CInfo*, int*, unsigned int*);
+static assign5_fn pick_assign5(int TS, bool update, int tps, bool fuse = false);
 
 static thread_local std::string g_err;
 static int set_err(int code, const std::string& msg) {
@@ -318,8 +318,9 @@ static int create_impl(int device, int H, int W, int K, int max_batch, bool cca_
     for (int ts : {128, 192, 256})
         for (int upd = 0; upd < 2; upd++)
             for (int tps : {1, 4})
-                CKC(cudaFuncSetAttribute(pick_assign5(ts, upd != 0, tps), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         c->max_smem_optin - 1024));
+                for (int fuse = 0; fuse <= upd; fuse++)
+                    CKC(cudaFuncSetAttribute(pick_assign5(ts, upd != 0, tps, fuse != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             c->max_smem_optin - 1024));
     if (const char* e = getenv("FSLIC_ASSIGN")) c->assign_impl = atoi(e) == 4 ? 4 : 5;
     CKC(cudaFuncSetAttribute(k_cca_select, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin - 4 * 1024));
     CKC(cudaFuncSetAttribute(k_debug_heap_select, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin - 4 * 1024));
@@ -430,7 +431,10 @@ static int run_cca(fslic_ctx* c, const uint16_t* d_in, uint16_t* d_out, int batc
         k_ccl_flatten<<<g, 256, 0, st>>>(cp, in, c->par, c->aux, c->blkcnt, c->rootbuf);
         k_scan_blocks<<<nb, 1024, 0, st>>>(c->blkcnt, c->blkoff, cp.nblk, cp.nblk, nullptr, 0, 1,
                                            &c->counters[0].ncomp, (int)(sizeof(CcaCounters) / sizeof(int)), nullptr, -1);
-        k_ccl_number<<<dim3(CCA_NUMBER_GRID, nb), CCA_BLOCK, 0, st>>>(cp, c->rootbuf, c->aux, c->blkcnt, c->blkoff, c->cleader, c->carea,
+        // grids of the per-component walks: sized for full batches (a few CTAs per image); a small batch gets more
+        // CTAs per image instead, it is all dependent-load latency there
+        const int number_grid = nb >= 8 ? CCA_NUMBER_GRID : std::min(std::max(ceil_div(cp.nblk, 32), CCA_NUMBER_GRID), 64);
+        k_ccl_number<<<dim3(number_grid, nb), CCA_BLOCK, 0, st>>>(cp, c->rootbuf, c->aux, c->blkcnt, c->blkoff, c->cleader, c->carea,
                                                                       c->counters, c->ahist);
         if (timed) CK(cudaEventRecord(c->cev[2], st));
         k_cca_threshold<<<nb, 1024, 0, st>>>(cp, c->carea, c->counters, c->ahist);
@@ -443,14 +447,14 @@ static int run_cca(fslic_ctx* c, const uint16_t* d_in, uint16_t* d_out, int batc
         auto tail = [&](int which, cudaStream_t ts) {
             CcaParams cq = cp;
             cq.which = which;
-            const dim3 gk(cp.nblk < CCA_KEPT_GRID ? cp.nblk : CCA_KEPT_GRID, nb);
+            const dim3 gk(std::min(cp.nblk, std::max(CCA_KEPT_GRID, 256 / nb)), nb);
             k_kept_count<<<gk, CCA_BLOCK, 0, ts>>>(cq, c->carea, c->counters, c->blkcnt);
             k_scan_blocks<<<nb, 1024, 0, ts>>>(c->blkcnt, c->blkoff, cp.nblk, 0, &c->counters[0].ncomp,
                                                (int)(sizeof(CcaCounters) / sizeof(int)), CCA_BLOCK,
                                                &c->counters[0].nkept, (int)(sizeof(CcaCounters) / sizeof(int)),
                                                c->counters, which);
             k_kept_label<<<gk, CCA_BLOCK, 0, ts>>>(cq, c->carea, c->counters, c->blkoff, c->cnew);
-            int ab = ceil_div(N, 256 * 8);
+            int ab = ceil_div(N, 256 * (nb < 4 ? 2 : 8));
             if (ab > c->num_sms * 8) ab = c->num_sms * 8;
             dim3 ga(ab, nb);
             if (timed) cudaEventRecord(c->cev[4], ts);
@@ -583,15 +587,16 @@ static assign_fn pick_assign(int TS, int stride, bool update) {
 
 // kernel menu of the TMA-staged kernel: TS in {128,192,256} x (stride 3 + update | stride 1, no update) x TPS in {1,4}
 template <int TS>
-static assign5_fn pick_assign5_ts(bool update, int tps) {
+static assign5_fn pick_assign5_ts(bool update, int tps, bool fuse) {
+    if (update && fuse) return tps == 4 ? k_assign5<TS, 3, true, 4, true> : k_assign5<TS, 3, true, 1, true>;
     if (update) return tps == 4 ? k_assign5<TS, 3, true, 4> : k_assign5<TS, 3, true, 1>;
     return tps == 4 ? k_assign5<TS, 1, false, 4> : k_assign5<TS, 1, false, 1>;
 }
-static assign5_fn pick_assign5(int TS, bool update, int tps) {
+static assign5_fn pick_assign5(int TS, bool update, int tps, bool fuse) {
     switch (TS) {
-        case 128: return pick_assign5_ts<128>(update, tps);
-        case 192: return pick_assign5_ts<192>(update, tps);
-        default: return pick_assign5_ts<256>(update, tps);
+        case 128: return pick_assign5_ts<128>(update, tps, fuse);
+        case 192: return pick_assign5_ts<192>(update, tps, fuse);
+        default: return pick_assign5_ts<256>(update, tps, fuse);
     }
 }
 
@@ -661,9 +666,13 @@ static int build_patches(fslic_ctx* c, int stride, bool need_sub, float coef, cu
     return FSLIC_OK;
 }
 
+// fuse_clusters / fused_out: when the TMA kernel takes an update pass of a small batch, its last CTA also does the
+// bookkeeping for the NEXT pass (prepare_in_tail) on these cluster records; *fused_out tells the caller to skip k_prepare.
 static int run_assign_pass(fslic_ctx* c, int batch, int stride, int rem, int cfg_stride, int fresh_from, bool update,
                            float coef, cudaStream_t st, int* launches, int variant = -1,
-                           const fslic_cluster* d_clusters = nullptr) {
+                           const fslic_cluster* d_clusters = nullptr, fslic_cluster* fuse_clusters = nullptr,
+                           bool* fused_out = nullptr) {
+    if (fused_out) *fused_out = false;
     if (variant >= 0) {  // float-distance variants (realdist.cuh): one thread per pixel over the cell grid
         AssignParams ap;
         memset(&ap, 0, sizeof(ap));
@@ -705,6 +714,7 @@ static int run_assign_pass(fslic_ctx* c, int batch, int stride, int rem, int cfg
     ap.ntiles = ap.tiles_x * ap.tiles_y;
     ap.coef = coef;
     ap.tps = AS_T;
+    ap.fuse_prepare = 0;
     // The TMA-staged kernel: row strides of the tensor maps must be multiples of 16 bytes (W % 8 == 0 for the u16
     // labels), the sub-row pitch is an immediate of its patch loads (stride 3 with the update, 1 without), and its
     // per-warp shared blocks must fit beside the patch.  Everything else takes the LDG kernel below.
@@ -738,7 +748,6 @@ static int run_assign_pass(fslic_ctx* c, int batch, int stride, int rem, int cfg
             use5 = false;
         } else {
             const uint16_t* tbl = c->sptable + (update ? 0 : SPT_MAX_ELEMS);
-            const assign5_fn fn = pick_assign5(g.TS, update, tps);
             const long supers = (long)ceil_div(ap.tiles_x, tps) * ap.tiles_y * batch;
             // Super tiles are handed out statically, so a launch lasts ceil(supers / warps) rounds: with ~4 rounds (720p x 32)
             // a full grid of 32-warp CTAs idles a fifth of the time in the last round.  The kernel is issue bound and
@@ -757,6 +766,23 @@ static int run_assign_pass(fslic_ctx* c, int batch, int stride, int rem, int cfg
                 warps5 = best_w;
                 smem5 = align_up((size_t)g.tbl_elems * 2, 128) + (size_t)warps5 * A5_WBLK;
             }
+            else if (supers < (long)c->num_sms * warps5) {
+                // not even one super tile per warp (single images): spread them over all SMs instead of filling a few
+                const int w = std::max(4, (int)ceil_div((int)supers, c->num_sms));
+                if (w < warps5) {
+                    warps5 = w;
+                    smem5 = align_up((size_t)g.tbl_elems * 2, 128) + (size_t)warps5 * A5_WBLK;
+                }
+            }
+            static const bool fuse_allowed = !(getenv("FSLIC_FUSE") && atoi(getenv("FSLIC_FUSE")) == 0);
+            const size_t tail_smem = prepare_tail_smem_bytes(c->K, c->ncell);
+            if (update && fuse_clusters && fused_out && fuse_allowed && batch <= 2 && c->K <= 4096 &&
+                tail_smem <= (size_t)(c->max_smem_optin - 1024)) {
+                ap.fuse_prepare = 1;
+                if (smem5 < tail_smem) smem5 = tail_smem;
+                *fused_out = true;
+            }
+            const assign5_fn fn = pick_assign5(g.TS, update, tps, ap.fuse_prepare != 0);
             long grid = (supers + warps5 - 1) / warps5;
             if (grid > c->num_sms) grid = c->num_sms;
             // the warp-uniform walk constants (constant bank; see the note on code generation in assign5.cuh)
@@ -782,7 +808,8 @@ static int run_assign_pass(fslic_ctx* c, int batch, int stride, int rem, int cfg
                 e1 = c->kev[c->kev_used++];
                 CK(cudaEventRecord(e0, st));
             }
-            fn<<<(int)grid, 32 * warps5, smem5, st>>>(ap, tmq, tml, qbase, lbase, SL_CINFO(c), SL_CELLS(c), SL_ACC(c), tbl);
+            fn<<<(int)grid, 32 * warps5, smem5, st>>>(ap, tmq, tml, qbase, lbase, SL_CINFO(c), SL_CELLS(c), SL_ACC(c), tbl,
+                                                      fuse_clusters, SL_CINFO(c), SL_CELLS(c), c->prep_tickets + c->slice);
             if (e1) CK(cudaEventRecord(e1, st));
             c->last_assign_impl = 5;
         }
@@ -893,16 +920,22 @@ static int iterate_front(fslic_ctx* c, int b0, const uint8_t* d_images, fslic_cl
     }
     const fslic_cluster* cl = d_clusters;  // the NoQ variant reads its float centroids from the cluster records themselves
     int rem = 0;
+    bool prepared = false;  // the previous assign+update launch already did the bookkeeping in its tail
     for (int it = 0; it < p->max_iter; it++) {
-        rc = run_prepare(c, d_clusters, batch, it == 0, it > 0, st, launches, noq);
-        if (rc) return rc;
-        rc = run_assign_pass(c, batch, stride, rem, stride, it, true, coef, st, launches, variant, cl);
+        if (!prepared) {
+            rc = run_prepare(c, d_clusters, batch, it == 0, it > 0, st, launches, noq);
+            if (rc) return rc;
+        }
+        rc = run_assign_pass(c, batch, stride, rem, stride, it, true, coef, st, launches, variant, cl,
+                             variant < 0 ? d_clusters : nullptr, &prepared);
         if (rc) return rc;
         rem = (rem + 1) % stride;
     }
     if (timing) CK(cudaEventRecord(c->ev[2], st));
-    rc = run_prepare(c, d_clusters, batch, p->max_iter == 0, p->max_iter > 0, st, launches, noq);
-    if (rc) return rc;
+    if (!prepared) {
+        rc = run_prepare(c, d_clusters, batch, p->max_iter == 0, p->max_iter > 0, st, launches, noq);
+        if (rc) return rc;
+    }
     rc = run_assign_pass(c, batch, 1, 0, stride, p->max_iter < stride ? p->max_iter : stride, false, coef, st, launches,
                          variant, cl);
     c->slice = 0;
