@@ -2,8 +2,8 @@
 
 Mirrors /root/reference/fast_slic/base_slic.py:3-62 (BaseSlic / Slic: same kwargs, defaults,
 properties, return dtype) and the Cython ``SlicModel`` (/root/reference/cfast_slic.pyx:15-260,
-attributes cfast_slic.pxd:104-120).  Only the default integer-distance path of the north star is
-implemented; the float-distance / LSC / preemptive variants raise NotImplementedError.
+attributes cfast_slic.pxd:104-120).  Implemented: the default integer-distance path of the north star, the
+float-distance variants and `preemptive`; LSC raises NotImplementedError.
 """
 import collections
 import contextlib
@@ -188,8 +188,8 @@ class SlicModel(object):
             raise NotImplementedError("real_dist_type %r (LSC) is outside the CUDA hot path" % (self.real_dist_type,))
         if self.real_dist and self.real_dist_type == "noq" and not self.manhattan_spatial_dist:
             raise NotImplementedError("SlicRealDistNoQ with manhattan_spatial_dist=False is outside the CUDA hot path")
-        if self.preemptive:
-            raise NotImplementedError("preemptive=True is outside the CUDA hot path")
+        if self.preemptive and self.real_dist:
+            raise NotImplementedError("preemptive=True together with a float-distance variant is outside the CUDA hot path")
         if not self.manhattan_spatial_dist:
             raise NotImplementedError("manhattan_spatial_dist=False is outside the CUDA hot path")
 
@@ -212,7 +212,7 @@ class SlicModel(object):
         H, W, _ = image.shape
         params = Engine.params(compactness, min_size_factor, subsample_stride, self.convert_to_lab, max_iter,
                                collect_timing=1)
-        if self.real_dist:
+        if self.real_dist or self.preemptive:
             return self._iterate_real_dist(image, params)
         clusters = np.ascontiguousarray(self._clusters)[None]
         # the lock covers the timing read-out too: it belongs to this call, not to another thread's next one
@@ -237,13 +237,17 @@ class SlicModel(object):
 
 
 def _iterate_real_dist(self, image, params):
-    """cfast_slic.pyx:198-252: the float-distance contexts, through fslic_b200_iterate_real (device buffers)."""
+    """cfast_slic.pyx:198-252: the float-distance contexts (fslic_b200_iterate_real) and the `preemptive` option
+    (fslic_b200_iterate_preemptive), both through device buffers."""
     H, W, _ = image.shape
     with _locked(lambda: get_engine(H, W, self._num_components, 1, self.device)) as eng:
         with torch.cuda.device(eng.device):
             img = torch.from_numpy(image).to(eng.device)[None]
             cl = torch.from_numpy(np.ascontiguousarray(self._clusters).view(np.uint8).reshape(1, -1, 32).copy()).to(eng.device)
-            labels = eng.iterate_real(self.real_dist_type, img, cl, params)
+            if self.preemptive:  # cfast_slic.pyx:183-184
+                labels = eng.iterate_preemptive(img, cl, params, self.preemptive_thres)
+            else:
+                labels = eng.iterate_real(self.real_dist_type, img, cl, params)
             ms = eng.stage_ms()
             self._clusters = cl[0].cpu().numpy().view(CLUSTER_DTYPE).reshape(-1)
             out = labels[0].cpu().numpy()

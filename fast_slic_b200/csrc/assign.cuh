@@ -30,6 +30,10 @@ struct PrepParams {
     int finalize;  // 1: fold `acc` into the clusters
     int last;      // 1: after the final update: set is_active / is_updatable like the reference leaves them
     int noq;       // 1: ContextRealDistNoQ -- centroids are float quotients, not rounded integers (context.cpp:375-381)
+    // k_prepare only: the `preemptive` option (preempt.cuh; preemptive.h:113-141, context.cpp:360)
+    int preempt;       // 1: only updatable clusters take their new centre; the movement test counts is_updatable down
+    float l1_thres;    // max(roundf(2 S thres), 1)
+    int* nactive;      // [B] number of active clusters (first pass: K = everything active)
 };
 
 __global__ void __launch_bounds__(1024) k_prepare(PrepParams pp, fslic_cluster* __restrict__ clusters,
@@ -48,6 +52,7 @@ __global__ void __launch_bounds__(1024) k_prepare(PrepParams pp, fslic_cluster* 
     int* cs = cell_start + (size_t)b * (pp.ncell + 1);
 
     for (int c = tid; c <= pp.ncell; c += nt) s_cnt[c] = 0;
+    if (pp.preempt && pp.first && tid == 0) pp.nactive[b] = pp.K;  // b_all_active = true (preemptive.h:63)
     __syncthreads();
 
     for (int k = tid; k < pp.K; k += nt) {
@@ -55,8 +60,10 @@ __global__ void __launch_bounds__(1024) k_prepare(PrepParams pp, fslic_cluster* 
         if (pp.finalize) {
             // packed sums: [0] = n | sum_y << 32, [1] = sum_x | sum_L << 32, [2] = sum_a | sum_b << 32
             const unsigned long long w0 = ac[k * 4 + 0], w1 = ac[k * 4 + 1], w2 = ac[k * 4 + 2];
-            const uint32_t n = (uint32_t)w0;
-            c.num_members = n;  // written even when n == 0 (context.cpp:360-362)
+            const float old_y = c.y, old_x = c.x;  // set_old_clusters (context.cpp:303): the centres the assign used
+            const bool frozen = pp.preempt && !c.is_updatable;  // context.cpp:360: keeps centre AND member count
+            const uint32_t n = frozen ? 0u : (uint32_t)w0;
+            if (!frozen) c.num_members = n;  // written even when n == 0 (context.cpp:360-362)
             if (n > 0 && pp.noq) {  // (float)sum / n: int -> float conversion, IEEE division
                 const float fn = __int2float_rn((int32_t)n);
                 c.y = __fdiv_rn(__int2float_rn((int32_t)(w0 >> 32)), fn);
@@ -73,6 +80,10 @@ __global__ void __launch_bounds__(1024) k_prepare(PrepParams pp, fslic_cluster* 
                 c.b = (float)(((int32_t)(w2 >> 32) + half) / in);
             }
             ac[k * 4 + 0] = 0; ac[k * 4 + 1] = 0; ac[k * 4 + 2] = 0;
+            if (pp.preempt && c.is_updatable) {  // PreemptiveGrid::set_new_clusters, first loop (preemptive.h:132-141)
+                const float l1 = __fadd_rn(fabsf(__fsub_rn(old_x, c.x)), fabsf(__fsub_rn(old_y, c.y)));
+                c.is_updatable = l1 < pp.l1_thres ? (uint8_t)(c.is_updatable - 1) : (uint8_t)2;
+            }
         }
         if (pp.first) {
             int y = min(max((int)c.y, 0), pp.H - 1), x = min(max((int)c.x, 0), pp.W - 1);
@@ -85,8 +96,12 @@ __global__ void __launch_bounds__(1024) k_prepare(PrepParams pp, fslic_cluster* 
         c.x = fminf(fmaxf(c.x, 0.f), (float)(pp.W - 1));
         c.y = fminf(fmaxf(c.y, 0.f), (float)(pp.H - 1));
         c.number = (uint16_t)k;
-        c.is_active = 1;
-        c.is_updatable = 2;
+        if (!pp.preempt || pp.first) {
+            c.is_active = 1;
+            c.is_updatable = 2;  // PreemptiveGrid::initialize (preemptive.h:59-67)
+        } else if (pp.last) {
+            c.is_active = 1;     // PreemptiveGrid::finalize (preemptive.h:69-74); is_updatable stays where it got to
+        }                        // else: k_preempt_mark decides is_active from the new centres
         cl[k] = c;
 
         const int cy = (int16_t)c.y, cx = (int16_t)c.x;

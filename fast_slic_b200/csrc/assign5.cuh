@@ -530,6 +530,7 @@ __global__ void __launch_bounds__(32 * A5_MAXWARPS, 1)
             pp.H = ap.H; pp.W = ap.W; pp.K = ap.K; pp.S = ap.S; pp.T = 2 * ap.S + 32;
             pp.G = ap.G; pp.cellW = ap.cellW; pp.cellH = ap.cellH; pp.ncell = ap.ncell;
             pp.first = 0; pp.finalize = 1; pp.last = 0; pp.noq = 0;
+            pp.preempt = 0; pp.l1_thres = 0.f; pp.nactive = nullptr;
             for (int bi = 0; bi < ap.B; bi++)
                 prepare_in_tail(pp, clusters + (size_t)bi * ap.K, acc + (size_t)bi * ap.K * 4, cinfo_next + (size_t)bi * ap.K,
                                 cell_start_next + (size_t)bi * (ap.ncell + 1), smem_raw, (int)threadIdx.x, (int)blockDim.x);

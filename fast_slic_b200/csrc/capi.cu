@@ -16,6 +16,7 @@
 #include "assign5.cuh"
 #include "graph.cuh"
 #include "realdist.cuh"
+#include "preempt.cuh"
 #include "cca.cuh"
 #include "common.cuh"
 #include "lab.cuh"
@@ -103,6 +104,10 @@ struct fslic_ctx {
     uint16_t* d_lab = nullptr;
     cudaStream_t own_stream = nullptr, in_stream = nullptr, out_stream = nullptr, side_stream = nullptr;
     cudaEvent_t side_fork = nullptr, side_join = nullptr, tail_done = nullptr;
+    // the `preemptive` option (preempt.cuh), allocated at the first such call
+    uint8_t* pre_cellmap = nullptr;     // [B][ceil(H/2S) * ceil(W/2S)] active 2S x 2S cells
+    int* pre_nactive = nullptr;         // [B] active clusters
+    float preempt_l1 = 0.f;             // max(roundf(2 S thres), 1) of the call in progress
     long long* selprof = nullptr;       // FSLIC_SELPROF=1: 8 words per image written by k_cca_select (diagnostics)
     CcaCounters* h_counters = nullptr;  // pinned, 64 entries: lets the host path learn which images need the replay
     std::vector<cudaEvent_t> pipe_ev;  // [2 * chunks]: input-ready / compute-done events of iterate_host
@@ -200,6 +205,8 @@ extern "C" int fslic_b200_destroy(fslic_ctx* c) {
     if (c->gexec) cudaGraphExecDestroy(c->gexec);
     if (c->h_counters) cudaFreeHost(c->h_counters);
     if (c->selprof) cudaFree(c->selprof);
+    if (c->pre_cellmap) cudaFree(c->pre_cellmap);
+    if (c->pre_nactive) cudaFree(c->pre_nactive);
     for (auto& e : c->pipe_ev) cudaEventDestroy(e);
     delete c;
     return FSLIC_OK;
@@ -673,6 +680,29 @@ static int run_assign_pass(fslic_ctx* c, int batch, int stride, int rem, int cfg
                            const fslic_cluster* d_clusters = nullptr, fslic_cluster* fuse_clusters = nullptr,
                            bool* fused_out = nullptr) {
     if (fused_out) *fused_out = false;
+    if (variant == 3 && update) {  // the `preemptive` option (preempt.cuh); its full assign is the ordinary one
+        AssignParams ap;
+        memset(&ap, 0, sizeof(ap));
+        ap.H = c->H; ap.W = c->W; ap.K = c->K; ap.S = c->S; ap.B = batch;
+        ap.stride = stride; ap.rem = rem;
+        ap.nsub = (c->H - rem + stride - 1) / stride;
+        if (ap.nsub <= 0) return FSLIC_OK;
+        ap.cfg_stride = cfg_stride; ap.fresh_from = fresh_from;
+        ap.G = c->G; ap.cellW = c->cellW; ap.cellH = c->cellH; ap.ncell = c->ncell;
+        ap.coef = coef;
+        const long px = (long)ap.nsub * c->W * batch;
+        long grid = (px + 255) / 256;
+        if (grid > (long)c->num_sms * 32) grid = (long)c->num_sms * 32;
+        const int CW2 = ceil_div(c->W, 2 * c->S), ncell2 = CW2 * ceil_div(c->H, 2 * c->S);
+        k_assign_preempt<true><<<(int)grid, 256, 0, st>>>(ap, SL_QUAD(c), SL_LABELS(c), SL_CINFO(c), SL_CELLS(c), d_clusters,
+                                                          SL_ACC(c), c->pre_cellmap + (size_t)c->slice * ncell2, CW2, ncell2,
+                                                          c->pre_nactive + c->slice);
+        c->last_assign_impl = 0;
+        if (launches) *launches += 1;
+        CK(cudaGetLastError());
+        return FSLIC_OK;
+    }
+    if (variant == 3) variant = -1;
     if (variant >= 0) {  // float-distance variants (realdist.cuh): one thread per pixel over the cell grid
         AssignParams ap;
         memset(&ap, 0, sizeof(ap));
@@ -860,12 +890,27 @@ static int run_assign_pass(fslic_ctx* c, int batch, int stride, int rem, int cfg
 }
 
 static int run_prepare(fslic_ctx* c, fslic_cluster* d_clusters, int batch, int first, int finalize, cudaStream_t st,
-                       int* launches, int noq = 0) {
+                       int* launches, int noq = 0, int preempt = 0, int last = 0) {
     PrepParams pp;
     pp.H = c->H; pp.W = c->W; pp.K = c->K; pp.S = c->S; pp.T = 2 * c->S + 32;
     pp.G = c->G; pp.cellW = c->cellW; pp.cellH = c->cellH; pp.ncell = c->ncell;
-    pp.first = first; pp.finalize = finalize; pp.last = 0; pp.noq = noq;
+    pp.first = first; pp.finalize = finalize; pp.last = last; pp.noq = noq;
+    pp.preempt = preempt; pp.l1_thres = c->preempt_l1; pp.nactive = preempt ? c->pre_nactive + c->slice : nullptr;
     const size_t smem = (size_t)(c->ncell + 2) * sizeof(int);
+    if (preempt) {  // k_prepare carries the option's bookkeeping; after an update k_preempt_mark derives the active set
+        k_prepare<<<batch, 1024, smem, st>>>(pp, d_clusters, SL_ACC(c), SL_QUAD(c), SL_CINFO(c), SL_CELLS(c),
+                                             c->cinfo_tmp + (size_t)c->slice * c->K);
+        if (launches) *launches += 1;
+        if (finalize && !last) {
+            const int CW2 = ceil_div(c->W, 2 * c->S), ncell2 = CW2 * ceil_div(c->H, 2 * c->S);
+            k_preempt_mark<<<batch, 1024, 0, st>>>(c->K, c->S, c->H, c->W, c->G, c->cellW, c->cellH, c->ncell, d_clusters, SL_CINFO(c),
+                                                   SL_CELLS(c), c->pre_cellmap + (size_t)c->slice * ncell2, CW2, ncell2,
+                                                   c->pre_nactive + c->slice);
+            if (launches) *launches += 1;
+        }
+        CK(cudaGetLastError());
+        return FSLIC_OK;
+    }
     // k_prepare2 (one thread per cluster, several CTAs per image) is quicker for a handful of images (single image:
     // 0.412 vs 0.431 ms per blocking call); with a full batch its extra CTAs only contend (18 vs 13 us at 32 images)
     static const int forced = getenv("FSLIC_PREPARE") ? atoi(getenv("FSLIC_PREPARE")) : 0;
@@ -914,7 +959,8 @@ static int iterate_front(fslic_ctx* c, int b0, const uint8_t* d_images, fslic_cl
     if (timing) CK(cudaEventRecord(c->ev[1], st));
     const int stride = p->subsample_stride;
     const int noq = variant == 2 ? 1 : 0;
-    if (variant < 0) {
+    const int preempt = variant == 3 ? 1 : 0;
+    if (variant < 0 || preempt) {
         rc = build_patches(c, stride, p->max_iter > 0, coef, st, launches);
         if (rc) return rc;
     }
@@ -923,7 +969,7 @@ static int iterate_front(fslic_ctx* c, int b0, const uint8_t* d_images, fslic_cl
     bool prepared = false;  // the previous assign+update launch already did the bookkeeping in its tail
     for (int it = 0; it < p->max_iter; it++) {
         if (!prepared) {
-            rc = run_prepare(c, d_clusters, batch, it == 0, it > 0, st, launches, noq);
+            rc = run_prepare(c, d_clusters, batch, it == 0, it > 0, st, launches, noq, preempt, 0);
             if (rc) return rc;
         }
         rc = run_assign_pass(c, batch, stride, rem, stride, it, true, coef, st, launches, variant, cl,
@@ -933,7 +979,7 @@ static int iterate_front(fslic_ctx* c, int b0, const uint8_t* d_images, fslic_cl
     }
     if (timing) CK(cudaEventRecord(c->ev[2], st));
     if (!prepared) {
-        rc = run_prepare(c, d_clusters, batch, p->max_iter == 0, p->max_iter > 0, st, launches, noq);
+        rc = run_prepare(c, d_clusters, batch, p->max_iter == 0, p->max_iter > 0, st, launches, noq, preempt, 1);
         if (rc) return rc;
     }
     rc = run_assign_pass(c, batch, 1, 0, stride, p->max_iter < stride ? p->max_iter : stride, false, coef, st, launches,
@@ -1030,6 +1076,30 @@ extern "C" int fslic_b200_iterate_real(fslic_ctx* c, int variant, const uint8_t*
                                        uint16_t* d_labels, int batch, const fslic_params* p, void* stream) {
     if (variant < 0 || variant > 2) return set_err(FSLIC_EINVAL, "variant must be 0 (standard), 1 (l2) or 2 (noq)");
     return iterate_plain(c, d_images, d_clusters, d_labels, batch, p, stream, false, variant);
+}
+
+extern "C" int fslic_b200_iterate_preemptive(fslic_ctx* c, const uint8_t* d_images, fslic_cluster* d_clusters, uint16_t* d_labels,
+                                             int batch, const fslic_params* p, float preemptive_thres, void* stream) {
+    int rc = check_batch(c, batch);
+    if (rc) return rc;
+    if (c->S <= 0) return set_err(FSLIC_EINVAL, "preemptive needs S >= 1 (the reference divides by 2 S, preemptive.h:37-38)");
+    if (!(preemptive_thres >= 0.f)) return set_err(FSLIC_EINVAL, "preemptive_thres must be >= 0");
+    USE_DEVICE(c->device);
+    if (!c->pre_cellmap) {
+        const size_t ncell2 = (size_t)ceil_div(c->W, 2 * c->S) * ceil_div(c->H, 2 * c->S);
+        uint8_t* cm = nullptr;
+        int* na = nullptr;
+        if (cudaMalloc(reinterpret_cast<void**>(&cm), ncell2 * c->maxB) != cudaSuccess ||
+            cudaMalloc(reinterpret_cast<void**>(&na), sizeof(int) * c->maxB) != cudaSuccess) {
+            if (cm) cudaFree(cm);
+            cudaGetLastError();
+            return set_err(FSLIC_ENOMEM, "out of device memory (preemptive scratch)");
+        }
+        c->pre_cellmap = cm;
+        c->pre_nactive = na;
+    }
+    c->preempt_l1 = fmaxf(roundf((float)(2 * c->S) * preemptive_thres), 1.0f);  // preemptive.h:126
+    return iterate_plain(c, d_images, d_clusters, d_labels, batch, p, stream, false, 3);
 }
 
 extern "C" int fslic_b200_assign_kernel_time(fslic_ctx* c, float* total_ms, int* launches) {

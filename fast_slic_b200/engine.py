@@ -116,6 +116,17 @@ class Engine:
                                                   _stream_ptr(self.device)))
         return labels
 
+    def iterate_preemptive(self, images, clusters, params, preemptive_thres, labels=None):
+        """`preemptive=True` of the reference (fslic_b200_iterate_preemptive); device tensors like iterate()."""
+        self._check_images(images)
+        B = images.shape[0]
+        if labels is None:
+            labels = torch.empty((B, self.H, self.W), dtype=torch.int16, device=self.device)
+        with self.lock:
+            check(self._L.fslic_b200_iterate_preemptive(self._h, images.data_ptr(), clusters.data_ptr(), labels.data_ptr(), B,
+                                                        C.byref(params), C.c_float(preemptive_thres), _stream_ptr(self.device)))
+        return labels
+
     def enforce_connectivity(self, labels, K, min_threshold):
         """In place on int16/uint16 labels [B,H,W] (cuda)."""
         B = labels.shape[0]

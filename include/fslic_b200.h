@@ -98,6 +98,13 @@ int fslic_b200_iterate(fslic_ctx* ctx, const uint8_t* d_images, fslic_cluster* d
 int fslic_b200_iterate_real(fslic_ctx* ctx, int variant, const uint8_t* d_images, fslic_cluster* d_clusters,
                             uint16_t* d_labels, int batch, const fslic_params* params, void* stream);
 
+/* == BaseContext::iterate with `preemptive = true` (context.h:32-33, preemptive.h; cfast_slic.pyx:183-184): clusters that
+ *    stop moving (L1 movement below max(round(2 S preemptive_thres), 1) pixels in two updates in a row) and have no
+ *    moving cluster within 2S stop being assigned and updated; `is_updatable` of the returned records holds the
+ *    countdown where it got to.  Same buffers as fslic_b200_iterate; bit-identical to the reference.  S >= 1. */
+int fslic_b200_iterate_preemptive(fslic_ctx* ctx, const uint8_t* d_images, fslic_cluster* d_clusters, uint16_t* d_labels,
+                                  int batch, const fslic_params* params, float preemptive_thres, void* stream);
+
 /* The same call as the reference-facing plugin makes it: HOST buffers in, HOST buffers out
  * (what SlicModel.iterate does with a numpy image, cfast_slic.pyx:150-260).  H2D copy, kernels and
  * D2H copy are pipelined over chunks of 32 images on three streams (pass pinned buffers for true overlap);

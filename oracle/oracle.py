@@ -82,16 +82,17 @@ class Port:
         return lut
 
     def iterate(self, image, clusters, max_iter=10, compactness=10.0, min_size_factor=0.25, stride=3,
-                convert_to_lab=True, stages=False):
+                convert_to_lab=True, stages=False, preemptive=False, preemptive_thres=0.05):
         image = np.ascontiguousarray(image)
         H, W, _ = image.shape
         K = len(clusters)
         out = np.zeros((H, W), np.uint16)
         quad = np.zeros((H, W, 4), np.uint8) if stages else None
         pre = np.zeros((H, W), np.uint16) if stages else None
-        self.lib.orc_iterate(H, W, K, _p(image, _u8p), clusters.ctypes.data_as(C.c_void_p), _p(out, _u16p),
-                             max_iter, C.c_float(compactness), C.c_float(min_size_factor), stride,
-                             int(convert_to_lab), _p(quad, _u8p), _p(pre, _u16p))
+        self.lib.orc_iterate_preemptive(H, W, K, _p(image, _u8p), clusters.ctypes.data_as(C.c_void_p), _p(out, _u16p),
+                                        max_iter, C.c_float(compactness), C.c_float(min_size_factor), stride,
+                                        int(convert_to_lab), int(bool(preemptive)), C.c_float(preemptive_thres),
+                                        _p(quad, _u8p), _p(pre, _u16p))
         return (out, quad, pre) if stages else out
 
     def enforce_connectivity(self, labels, K, thres):
@@ -173,13 +174,20 @@ class Ref:
         return clusters
 
     def iterate(self, image, clusters, max_iter=10, compactness=10.0, min_size_factor=0.25, stride=3,
-                convert_to_lab=True, stages=False, arch="x64/avx2", num_threads=-1):
+                convert_to_lab=True, stages=False, arch="x64/avx2", num_threads=-1, preemptive=False,
+                preemptive_thres=0.05):
         image = np.ascontiguousarray(image)
         H, W, _ = image.shape
         K = len(clusters)
         out = np.zeros((H, W), np.uint16)
         quad = np.zeros((H, W, 4), np.uint8) if stages else None
         pre = np.zeros((H, W), np.uint16) if stages else None
+        if preemptive:  # (no quad stage dump on this door; the Lab stage does not depend on the flag)
+            self.lib.ref_iterate_preemptive(1 if arch == "x64/avx2" else 0, H, W, K, _p(image, _u8p),
+                                            clusters.ctypes.data_as(C.c_void_p), _p(out, _u16p), max_iter,
+                                            C.c_float(compactness), C.c_float(min_size_factor), stride,
+                                            int(convert_to_lab), C.c_float(preemptive_thres), num_threads, _p(pre, _u16p))
+            return (out, quad, pre) if stages else out
         self.lib.ref_iterate(1 if arch == "x64/avx2" else 0, H, W, K, _p(image, _u8p),
                              clusters.ctypes.data_as(C.c_void_p), _p(out, _u16p), max_iter, C.c_float(compactness),
                              C.c_float(min_size_factor), stride, int(convert_to_lab), num_threads,

@@ -106,6 +106,29 @@ void ref_iterate(int arch, int H, int W, int K, const uint8_t* image, Cluster* c
     }
 }
 
+// the same call with preemptive = true (context.h:32-33; cfast_slic.pyx:183-184)
+void ref_iterate_preemptive(int arch, int H, int W, int K, const uint8_t* image, Cluster* clusters, uint16_t* out,
+                            int max_iter, float compactness, float min_size_factor, int stride, int convert_to_lab,
+                            float preemptive_thres, int num_threads, uint16_t* precca_out) {
+    if (arch == 1) {
+        ProbeAvx2 ctx(H, W, K, image, clusters);
+        configure(ctx, compactness, min_size_factor, stride, convert_to_lab, num_threads);
+        ctx.preemptive = true;
+        ctx.preemptive_thres = preemptive_thres;
+        ctx.initialize_state();
+        ctx.iterate(out, max_iter);
+        ctx.dump(nullptr, precca_out);
+    } else {
+        ProbeStd ctx(H, W, K, image, clusters);
+        configure(ctx, compactness, min_size_factor, stride, convert_to_lab, num_threads);
+        ctx.preemptive = true;
+        ctx.preemptive_thres = preemptive_thres;
+        ctx.initialize_state();
+        ctx.iterate(out, max_iter);
+        ctx.dump(nullptr, precca_out);
+    }
+}
+
 // cfast_slic.pyx:371-396 (K = max label + 1 is computed by the caller, as the pyx does)
 void ref_enforce_connectivity(uint16_t* labels, int H, int W, int K, int min_threshold, int num_threads) {
     fsparallel::Scope scope(num_threads);

@@ -274,13 +274,16 @@ static void assign_pass_bucketed(int H, int W, int K, int S, OrcCluster* cluster
 /* ------------------------------------------------------------------ */
 /* update: src/context.cpp:302-387 (all-active, quantised branch)      */
 /* ------------------------------------------------------------------ */
-static void update_pass(int H, int W, int K, OrcCluster* clusters, const uint8_t* quad, const uint16_t* assignment,
-                        int stride, int rem) {
+/* active_grid == NULL: every pixel counts (preemptive off, or preemptive_grid.all_active(), context.cpp:314-328);
+ * otherwise only pixels whose 2S x 2S cell is active (context.cpp:329-344, preemptive.h:109-111). */
+static void update_pass_masked(int H, int W, int K, OrcCluster* clusters, const uint8_t* quad, const uint16_t* assignment,
+                               int stride, int rem, const int* active_grid, int cell_pitch, int CW) {
     int32_t* n = (int32_t*)calloc((size_t)K, sizeof(int32_t));
     int32_t* acc = (int32_t*)calloc((size_t)K * 5, sizeof(int32_t));
     for (int i = rem; i < H; i += stride) { /* fit_to_stride(0) == rem, context.h:78-82 */
         for (int j = 0; j < W; j++) {
             long p = (long)i * W + j;
+            if (active_grid && !active_grid[CW * (i / cell_pitch) + (j / cell_pitch)]) continue;
             uint16_t c = assignment[p];
             if (c == 0xFFFF) continue;
             n[c]++;
@@ -304,6 +307,55 @@ static void update_pass(int H, int W, int K, OrcCluster* clusters, const uint8_t
     }
     free(n);
     free(acc);
+}
+static void update_pass(int H, int W, int K, OrcCluster* clusters, const uint8_t* quad, const uint16_t* assignment,
+                        int stride, int rem) {
+    update_pass_masked(H, W, K, clusters, quad, assignment, stride, rem, NULL, 1, 0);
+}
+
+/* ------------------------------------------------------------------ */
+/* PreemptiveGrid::set_new_clusters, src/preemptive.h:113-177.          */
+/* old_yx: the centres before this update (set_old_clusters, :105-108). */
+/* Cells are 2S x 2S pixels (:37-56).  A cluster that moved less than   */
+/* l1_thres counts its is_updatable down (2 -> 1 -> 0, and 0 stays 0);  */
+/* every cluster within a 2S Chebyshev distance (truncated centres) of  */
+/* a still-updatable one is active, and so is its cell.  Returns        */
+/* b_all_active.  The L1 movement is a float |.| here; the centres are  */
+/* integer valued in the quantised contexts, so whether the reference's */
+/* unqualified abs() resolves to the int or the float overload cannot   */
+/* change the result.                                                   */
+/* ------------------------------------------------------------------ */
+static int set_new_clusters(int H, int W, int K, int S, float thres, OrcCluster* clusters, const float* old_yx,
+                            int* active_grid) {
+    int CW = ceil_int(W, 2 * S), CH = ceil_int(H, 2 * S);
+    for (int c = 0; c < CW * CH; c++) active_grid[c] = 0;
+    for (int k = 0; k < K; k++) clusters[k].is_active = 0;                              /* :119-122 */
+    float l1_thres = roundf((float)(2 * S) * thres);                                    /* :126 */
+    if (l1_thres < 1.0f) l1_thres = 1.0f;
+    for (int k = 0; k < K; k++) {                                                       /* :132-141 */
+        if (!clusters[k].is_updatable) continue;
+        float l1 = fabsf(old_yx[2 * k + 1] - clusters[k].x) + fabsf(old_yx[2 * k] - clusters[k].y);
+        if (l1 < l1_thres) clusters[k].is_updatable--;
+        else clusters[k].is_updatable = 2;
+    }
+    for (int k = 0; k < K; k++) {                                                       /* :143-168 */
+        if (!clusters[k].is_updatable) continue;
+        int y = (int)clusters[k].y, x = (int)clusters[k].x;
+        int cy = y / (2 * S), cx = x / (2 * S);
+        for (int n = 0; n < K; n++) {  /* the reference walks the 3 x 3 cells around (cy, cx); same set, see below */
+            int ny = (int)clusters[n].y, nx = (int)clusters[n].x;
+            int ncy = ny / (2 * S), ncx = nx / (2 * S);
+            if (abs(ncy - cy) > 1 || abs(ncx - cx) > 1) continue;                       /* :150-156 */
+            if (abs(ny - y) <= 2 * S && abs(nx - x) <= 2 * S) {                         /* :160-161 */
+                clusters[n].is_active = 1;
+                active_grid[CW * ncy + ncx] = 1;
+            }
+        }
+    }
+    (void)CH;
+    int num_active = 0;
+    for (int k = 0; k < K; k++) num_active += clusters[k].is_active;                    /* :170-176 */
+    return num_active == K;
 }
 
 /* ------------------------------------------------------------------ */
@@ -438,9 +490,20 @@ void orc_enforce_connectivity(uint16_t* labels, int H, int W, int K, int min_thr
 /* the whole pipeline: src/context.cpp:109-197                         */
 /* quad_out (u8[H*W*4]) / precca_out (u16[H*W]) may be NULL.           */
 /* ------------------------------------------------------------------ */
+void orc_iterate_preemptive(int H, int W, int K, const uint8_t* image, OrcCluster* clusters, uint16_t* out, int max_iter,
+                            float compactness, float min_size_factor, int stride, int convert_to_lab, int preemptive,
+                            float preemptive_thres, uint8_t* quad_out, uint16_t* precca_out);
 void orc_iterate(int H, int W, int K, const uint8_t* image, OrcCluster* clusters, uint16_t* out, int max_iter,
                  float compactness, float min_size_factor, int stride, int convert_to_lab, uint8_t* quad_out,
                  uint16_t* precca_out) {
+    orc_iterate_preemptive(H, W, K, image, clusters, out, max_iter, compactness, min_size_factor, stride, convert_to_lab, 0,
+                           0.05f, quad_out, precca_out);
+}
+
+/* preemptive != 0: BaseContext with preemptive = true (context.h:32-33, preemptive.h) */
+void orc_iterate_preemptive(int H, int W, int K, const uint8_t* image, OrcCluster* clusters, uint16_t* out, int max_iter,
+                            float compactness, float min_size_factor, int stride, int convert_to_lab, int preemptive,
+                            float preemptive_thres, uint8_t* quad_out, uint16_t* precca_out) {
     if (H <= 0 || W <= 0 || K <= 0) return;
     int S = (int16_t)sqrt((double)(H * W / K)); /* context.h:60 -- integer division first */
     long N = (long)H * W;
@@ -459,12 +522,31 @@ void orc_iterate(int H, int W, int K, const uint8_t* image, OrcCluster* clusters
     for (long p = 0; p < N; p++) assignment[p] = 0xFFFF; /* :139-146 */
     orc_spatial_lut(S, compactness, color_shift, lut);    /* :147 */
     for (int k = 0; k < K; k++) clusters[k].is_updatable = 2; /* preemptive.h:59-67 (cooldown) */
+    int all_active = 1;                                        /* preemptive.h:63 */
+    int* active_grid = NULL;
+    float* old_yx = NULL;
+    if (preemptive && S > 0) {
+        active_grid = (int*)calloc((size_t)ceil_int(W, 2 * S) * ceil_int(H, 2 * S), sizeof(int));
+        old_yx = (float*)malloc(sizeof(float) * 2 * (size_t)K);
+    }
     int rem = 0;
     for (int it = 0; it < max_iter; it++) { /* :158-175 */
         assign_pass_bucketed(H, W, K, S, clusters, quad, lut, assignment, min_dists, stride, rem);
-        update_pass(H, W, K, clusters, quad, assignment, stride, rem);
+        if (active_grid) {
+            for (int k = 0; k < K; k++) { /* set_old_clusters, context.cpp:303 (after assign()'s clamp) */
+                old_yx[2 * k] = clusters[k].y;
+                old_yx[2 * k + 1] = clusters[k].x;
+            }
+            update_pass_masked(H, W, K, clusters, quad, assignment, stride, rem, all_active ? NULL : active_grid, 2 * S,
+                               ceil_int(W, 2 * S));
+            all_active = set_new_clusters(H, W, K, S, preemptive_thres, clusters, old_yx, active_grid); /* :385 */
+        } else {
+            update_pass(H, W, K, clusters, quad, assignment, stride, rem);
+        }
         rem = (rem + 1) % stride;
     }
+    free(active_grid);
+    free(old_yx);
     for (int k = 0; k < K; k++) clusters[k].is_active = 1; /* preemptive.h:69-74 */
     assign_pass_bucketed(H, W, K, S, clusters, quad, lut, assignment, min_dists, 1, 0); /* :178-181 */
     if (quad_out) memcpy(quad_out, quad, (size_t)N * 4);

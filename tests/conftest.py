@@ -53,12 +53,13 @@ class Checker:
         return self._impl.initialize(image, K)
 
     def iterate(self, image, clusters, max_iter=10, compactness=10.0, min_size_factor=0.25, stride=3,
-                convert_to_lab=True, stages=False):
+                convert_to_lab=True, stages=False, preemptive=False, preemptive_thres=0.05):
         if self.kind == "reference":
             return self._impl.iterate(image, clusters, max_iter, compactness, min_size_factor, stride, convert_to_lab,
-                                      stages=stages, arch="x64/avx2", num_threads=self._threads)
+                                      stages=stages, arch="x64/avx2", num_threads=self._threads, preemptive=preemptive,
+                                      preemptive_thres=preemptive_thres)
         return self._impl.iterate(image, clusters, max_iter, compactness, min_size_factor, stride, convert_to_lab,
-                                  stages=stages)
+                                  stages=stages, preemptive=preemptive, preemptive_thres=preemptive_thres)
 
     def iterate_real(self, variant, image, clusters, max_iter=10, compactness=10.0, min_size_factor=0.25, stride=3,
                      convert_to_lab=True, stages=False):

@@ -349,3 +349,27 @@ def test_oracle_real_dist_variants_match_compiled_reference(port, ref, variant):
         o1, p1 = port.iterate_real(variant, img, c1, *args, stages=True)
         o2, p2 = ref.iterate_real(variant, img, c2, *args, stages=True)
         assert (p1 == p2).all() and (o1 == o2).all() and c1.tobytes() == c2.tobytes(), (variant, kind, H, W, K)
+
+
+def test_oracle_preemptive_matches_compiled_reference(port, ref):
+    """PreemptiveGrid (preemptive.h) + the branches of assign / update that consult it (context.cpp:218, 307-385): the
+    restatement reproduces the compiled reference with preemptive = true -- pre-CCA labels, final labels, Cluster bytes
+    (is_updatable countdown included), both arch contexts -- and the option changes the result."""
+    for kind, H, W, K, thres, kw in [("syn", 120, 160, 48, 0.05, {}), ("syn", 200, 300, 150, 0.05, {}),
+                                     ("syn", 240, 320, 200, 0.2, dict(max_iter=15)),
+                                     ("syn", 181, 257, 90, 0.1, dict(subsample_stride=1, max_iter=6)),
+                                     ("blocks", 240, 320, 64, 0.5, dict(subsample_stride=2)),
+                                     ("syn", 300, 400, 300, 0.02, dict(sigma=4.0))]:
+        sigma, a = split_kwargs(kw)
+        img = make_image(kind, H, W, seed=43, sigma=sigma)
+        args = (a["max_iter"], a["compactness"], a["min_size_factor"], a["subsample_stride"], a["convert_to_lab"])
+        plain = ref.iterate(img, ref.initialize(img, K), *args)
+        for arch in ("x64/avx2", "standard"):
+            c1, c2 = port.initialize(img, K), ref.initialize(img, K)
+            for round_ in range(2):  # cold start, then warm start on the records the first call left
+                o1, _, p1 = port.iterate(img, c1, *args, stages=True, preemptive=True, preemptive_thres=thres)
+                o2, _, p2 = ref.iterate(img, c2, *args, stages=True, arch=arch, num_threads=2, preemptive=True,
+                                        preemptive_thres=thres)
+                assert (p1 == p2).all() and (o1 == o2).all() and c1.tobytes() == c2.tobytes(), (kind, H, W, K, thres, arch, round_)
+                if round_ == 0:
+                    assert (o2 != plain).any(), "the case does not exercise the option"

@@ -517,3 +517,37 @@ def test_real_dist_variants(checker, variant, case):
         gc = s.slic_model.cluster_array
         for f in ("y", "x", "r", "g", "b", "num_members", "number", "is_active", "is_updatable"):
             assert (gc[f] == cl[f]).all(), "%s round %d: cluster field %s" % (variant, round_, f)
+
+
+PREEMPT_CASES = [("syn", 120, 160, 48, 0.05, {}), ("syn", 200, 300, 150, 0.05, {}), ("syn", 240, 320, 200, 0.2, dict(max_iter=15)),
+                 ("syn", 181, 257, 90, 0.1, dict(subsample_stride=1, max_iter=6)), ("blocks", 240, 320, 64, 0.5, dict(subsample_stride=2)),
+                 ("syn", 300, 400, 300, 0.02, {}), ("noise", 120, 160, 48, 0.05, dict(min_size_factor=0.0)),
+                 ("syn", 480, 640, 400, 0.05, dict(sigma=4.0)), ("syn", 720, 1280, 1600, 0.05, dict(min_size_factor=0.0))]
+
+
+@pytest.mark.parametrize("case", PREEMPT_CASES, ids=lambda c: "%s_%dx%d_K%d_t%g" % c[:5])
+def test_preemptive(checker, case):
+    """Slic(preemptive=True, preemptive_thres=t) (fast_slic/base_slic.py:12-13 -> preemptive.h, context.cpp:218,307-385):
+    clusters that stopped moving drop out of assign and update.  Labels and the raw Cluster records -- including the
+    is_updatable countdown the reference leaves in them -- identical to the compiled reference, cold and warm start; the
+    option really bites (the result differs from the non-preemptive one)."""
+    import fast_slic_b200 as fs
+    kind, H, W, K, thres, kw = case
+    sigma, args = split_kwargs(kw)
+    img = make_image(kind, H, W, seed=43, sigma=sigma)
+    s = fs.Slic(num_components=K, compactness=args["compactness"], min_size_factor=args["min_size_factor"],
+                subsample_stride=args["subsample_stride"], convert_to_lab=args["convert_to_lab"], preemptive=True,
+                preemptive_thres=thres)
+    cl = checker.initialize(img, K)
+    plain = checker.iterate(img, checker.initialize(img, K), args["max_iter"], args["compactness"], args["min_size_factor"],
+                            args["subsample_stride"], args["convert_to_lab"])
+    for round_ in range(2):
+        got = s.iterate(img, args["max_iter"]).view(np.uint16)
+        want = checker.iterate(img, cl, args["max_iter"], args["compactness"], args["min_size_factor"], args["subsample_stride"],
+                               args["convert_to_lab"], preemptive=True, preemptive_thres=thres)
+        assert (got == want).all(), "round %d: %d px differ" % (round_, int((got != want).sum()))
+        gc = s.slic_model.cluster_array
+        for f in ("y", "x", "r", "g", "b", "num_members", "number", "is_active", "is_updatable"):
+            assert (gc[f] == cl[f]).all(), "round %d: cluster field %s" % (round_, f)
+        if round_ == 0 and kind != "noise":
+            assert (want != plain).any(), "the case does not exercise the option"
