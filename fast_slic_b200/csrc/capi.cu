@@ -411,6 +411,8 @@ static int run_cca(fslic_ctx* c, const uint16_t* d_in, uint16_t* d_out, int batc
     cp.nblk = ceil_div(N, CCA_BLOCK);
     const size_t heap_bytes = (size_t)(2 * K + 4) * 8;  // live slots + the +infinity padding of the replay loop
     cp.heap_in_smem = heap_bytes + SEL_CHUNK * 8 <= (size_t)(c->max_smem_optin - 8 * 1024);
+    static const int sel_sync = (getenv("FSLIC_SELSYNC") && atoi(getenv("FSLIC_SELSYNC")) == 0) ? 0 : 1;
+    cp.sel_sync = sel_sync;
     if (K + 2 > c->heap_K) return set_err(FSLIC_EINVAL, "K too large for the selection heap");
     for (int b0 = 0; b0 < batch; b0 += c->cca_batch) {
         const int nb = (batch - b0 < c->cca_batch) ? (batch - b0) : c->cca_batch;

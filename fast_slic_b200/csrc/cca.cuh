@@ -31,6 +31,7 @@ struct CcaParams {
     int thres;         // min_threshold
     int nblk;          // ceil(N / CCA_BLOCK)
     int heap_in_smem;  // k_cca_select keeps its heap in shared memory
+    int sel_sync;      // k_cca_select: warp barriers between the half-steps of the replay loop (FSLIC_SELSYNC, default 1)
     int which;         // post-selection kernels: -1 all images, 0 only images settled by k_cca_threshold, 1 only replayed ones
 };
 
@@ -676,7 +677,12 @@ __device__ __forceinline__ void hs_adjust_heap(const HeapMem<SMEM>& h, int hole,
 // with an earlier sift-down (possible right after a window reload) the hit simply stays where it is and is retried in
 // the next trip -- the root has not changed, and a sift-down ends within `depth` half-steps.
 #define SEL_CHILDREN "ld.volatile.shared.v4.u32 {a0, a1, b0, b1}, [c];\n\t"
-#define SEL_HALF_STEP                                                                                       \
+// BAR: "" or a bar.warp.sync behind the store.  The lanes exchange data through shared memory from one half-step to the
+// next; the CUDA memory model asks for a warp barrier in between.  On the hardware a warp's shared-memory instructions
+// execute in issue order and this loop never diverges (everything is predicated, its two branches test vote results),
+// so the barrier-free form computes the same thing ~10 % faster; FSLIC_SELSYNC=0 selects it, the default keeps the
+// barriers (compute-sanitizer racecheck clean).
+#define SEL_HALF_STEP(BAR)                                                                                  \
     "setp.gt.u32 tl, b1, a1;\n\t"            /* right child unless area[right] > area[left] */             \
     "min.u32 chi, a1, b1;\n\t"                                                                            \
     "selp.b32 clo, a0, b0, tl;\n\t"                                                                       \
@@ -684,6 +690,7 @@ __device__ __forceinline__ void hs_adjust_heap(const HeapMem<SMEM>& h, int hole,
     "min.u32 ohi, chi, vhi;\n\t"                                                                          \
     "selp.b32 olo, clo, vlo, mv;\n\t"                                                                     \
     "@act st.volatile.shared.v2.u32 [hole], {olo, ohi};\n\t" /* ... or the value lands here */             \
+    BAR                                                                                                   \
     "add.u32 c8, c, 8;\n\t"                                                                               \
     "selp.b32 nh, c, c8, tl;\n\t"                                                                         \
     "selp.b32 hole, nh, rooth, mv;\n\t"      /* idle lanes rest on the root: their loads are one broadcast */ \
@@ -691,76 +698,82 @@ __device__ __forceinline__ void hs_adjust_heap(const HeapMem<SMEM>& h, int hole,
     "sub.u32 c, t0, base;\n\t"               /* slot(h) = h + 1; children at slots 2h+2, 2h+3 */           \
     "mov.pred act, mv;\n\t"
 
+#define SEL_LOOP_ASM(BAR)                                                                                                   \
+    "{\n\t"                                                                                                                 \
+    ".reg .pred act, mv, tl, p, some, first, nact, take, kill, inq;\n\t"                                                    \
+    ".reg .b32 base, c, hole, vlo, vhi, a0, a1, b0, b1, chi, clo, ohi, olo, c8, nh, t0, t1, t2, root, hit, elo, ehi;\n\t"    \
+    ".reg .b32 lt, le, wpos, idx, qaddr, rooth, drain;\n\t"                                                                 \
+    "mov.u32 base, %2;\n\t"                                                                                                 \
+    "mov.u32 lt, %%lanemask_lt;\n\t"                                                                                        \
+    "mov.u32 le, %%lanemask_le;\n\t"                                                                                        \
+    "add.u32 rooth, base, 8;\n\t"     /* root = slot 1, its children = slots 2, 3 */                                        \
+    "mov.u32 hole, rooth;\n\t"                                                                                              \
+    "add.u32 c, base, 16;\n\t"                                                                                              \
+    "mov.u32 vlo, 0;\n\t"                                                                                                   \
+    "mov.u32 vhi, 0;\n\t"                                                                                                   \
+    "setp.ne.u32 act, 0, 0;\n\t"                                                                                            \
+    "mov.u32 wpos, %5;\n\t"                                                                                                 \
+    SEL_CHILDREN                                                                                                            \
+    "SEL_LOAD:\n\t"                    /* the window [wpos, wpos + 32) of the queue, one element per lane */                \
+    "add.u32 idx, wpos, %6;\n\t"                                                                                            \
+    "setp.lt.s32 inq, idx, %4;\n\t"                                                                                         \
+    "mov.u32 elo, 0;\n\t"                                                                                                   \
+    "mov.u32 ehi, 0;\n\t"              /* area 0 never beats the root: consumed / missing elements */                       \
+    "shl.b32 qaddr, idx, 3;\n\t"                                                                                            \
+    "add.u32 qaddr, qaddr, %3;\n\t"                                                                                         \
+    "@inq ld.shared.v2.u32 {elo, ehi}, [qaddr];\n\t"                                                                        \
+    "SEL_TRIP:\n\t"                                                                                                         \
+    "add.u32 %1, %1, 1;\n\t"                                                                                                \
+    SEL_HALF_STEP(BAR)                 /* (its children were loaded at the end of the previous trip) */                     \
+    "ld.volatile.shared.u32 root, [base+12];\n\t"  /* final: the newest sift-down has left level 0 */                       \
+    SEL_CHILDREN                                                                                                            \
+    SEL_HALF_STEP(BAR)                                                                                                      \
+    "setp.gt.u32 p, ehi, root;\n\t"    /* comp(i, first) of __heap_select */                                                \
+    "vote.sync.ballot.b32 hit, p, 0xffffffff;\n\t"                                                                          \
+    "vote.sync.any.pred some, p, 0xffffffff;\n\t"                                                                           \
+    SEL_CHILDREN                       /* of the next trip's first half-step: a lane that starts a sift-down now was */     \
+                                       /* resting on the root, so the addresses do not depend on the decision below */      \
+    "@!some bra.uni SEL_NEXT;\n\t"                                                                                          \
+    "and.b32 t1, hit, lt;\n\t"                                                                                              \
+    "setp.eq.and.u32 first, t1, 0, p;\n\t"                                                                                  \
+    "not.pred nact, act;\n\t"                                                                                               \
+    "and.pred take, first, nact;\n\t"                                                                                       \
+    "and.b32 t2, hit, le;\n\t"                                                                                              \
+    "setp.eq.or.u32 kill, t2, 0, take;\n\t"  /* elements in front of the first hit are gone for good */                     \
+    "@take mov.u32 vlo, elo;\n\t"                                                                                           \
+    "@take mov.u32 vhi, ehi;\n\t"                                                                                           \
+    "@take add.u32 %0, %0, 1;\n\t"                                                                                          \
+    "@kill mov.u32 ehi, 0;\n\t"                                                                                             \
+    "or.pred act, act, take;\n\t"                                                                                           \
+    "bra.uni SEL_TRIP;\n\t"                                                                                                 \
+    "SEL_NEXT:\n\t"                    /* nothing left in the window beats the root, and the root only grows */             \
+    "add.u32 wpos, wpos, 32;\n\t"                                                                                           \
+    "setp.lt.s32 inq, wpos, %4;\n\t"                                                                                        \
+    "@inq bra.uni SEL_LOAD;\n\t"                                                                                            \
+    "mov.u32 drain, %7;\n\t"           /* no sift-down takes more than `depth` half-steps */                                \
+    "SEL_DRAIN:\n\t"                                                                                                        \
+    SEL_HALF_STEP(BAR)                                                                                                      \
+    SEL_CHILDREN                                                                                                            \
+    "sub.u32 drain, drain, 1;\n\t"                                                                                          \
+    "setp.gt.s32 inq, drain, 0;\n\t"                                                                                        \
+    "@inq bra.uni SEL_DRAIN;\n\t"                                                                                           \
+    "}\n\t"
+
+template <bool WARPSYNC>
 __device__ __forceinline__ int sel_replay_smem(uint32_t heap_saddr, uint32_t queue_saddr, int qn, int consumed, int depth, int lane,
                                                long long& trips_out) {
     uint32_t cnt = 0, trips = 0;
     if (consumed < qn) {
-        // No bar.warp.sync between the half-steps: the loop has no divergent branch (everything is predicated, the two
-        // branches test vote results), the shared accesses are volatile (never reordered), and a warp's shared-memory
-        // instructions execute in issue order; vote.sync reconverges the warp once per trip anyway.
-        asm volatile(
-            "{\n\t"
-            ".reg .pred act, mv, tl, p, some, first, nact, take, kill, inq;\n\t"
-            ".reg .b32 base, c, hole, vlo, vhi, a0, a1, b0, b1, chi, clo, ohi, olo, c8, nh, t0, t1, t2, root, hit, elo, ehi;\n\t"
-            ".reg .b32 lt, le, wpos, idx, qaddr, rooth, drain;\n\t"
-            "mov.u32 base, %2;\n\t"
-            "mov.u32 lt, %%lanemask_lt;\n\t"
-            "mov.u32 le, %%lanemask_le;\n\t"
-            "add.u32 rooth, base, 8;\n\t"     // root = slot 1, its children = slots 2, 3
-            "mov.u32 hole, rooth;\n\t"
-            "add.u32 c, base, 16;\n\t"
-            "mov.u32 vlo, 0;\n\t"
-            "mov.u32 vhi, 0;\n\t"
-            "setp.ne.u32 act, 0, 0;\n\t"
-            "mov.u32 wpos, %5;\n\t"
-            SEL_CHILDREN
-            "SEL_LOAD:\n\t"                    // the window [wpos, wpos + 32) of the queue, one element per lane
-            "add.u32 idx, wpos, %6;\n\t"
-            "setp.lt.s32 inq, idx, %4;\n\t"
-            "mov.u32 elo, 0;\n\t"
-            "mov.u32 ehi, 0;\n\t"              // area 0 never beats the root: consumed / missing elements
-            "shl.b32 qaddr, idx, 3;\n\t"
-            "add.u32 qaddr, qaddr, %3;\n\t"
-            "@inq ld.shared.v2.u32 {elo, ehi}, [qaddr];\n\t"
-            "SEL_TRIP:\n\t"
-            "add.u32 %1, %1, 1;\n\t"
-            SEL_HALF_STEP                      // (its children were loaded at the end of the previous trip)
-            "ld.volatile.shared.u32 root, [base+12];\n\t"  // final: the newest sift-down has left level 0
-            SEL_CHILDREN
-            SEL_HALF_STEP
-            "setp.gt.u32 p, ehi, root;\n\t"    // comp(i, first) of __heap_select
-            "vote.sync.ballot.b32 hit, p, 0xffffffff;\n\t"
-            "vote.sync.any.pred some, p, 0xffffffff;\n\t"
-            SEL_CHILDREN                       // of the next trip's first half-step: a lane that starts a sift-down now was
-                                               // resting on the root, so the addresses do not depend on the decision below
-            "@!some bra.uni SEL_NEXT;\n\t"
-            "and.b32 t1, hit, lt;\n\t"
-            "setp.eq.and.u32 first, t1, 0, p;\n\t"
-            "not.pred nact, act;\n\t"
-            "and.pred take, first, nact;\n\t"
-            "and.b32 t2, hit, le;\n\t"
-            "setp.eq.or.u32 kill, t2, 0, take;\n\t"  // elements in front of the first hit are gone for good
-            "@take mov.u32 vlo, elo;\n\t"
-            "@take mov.u32 vhi, ehi;\n\t"
-            "@take add.u32 %0, %0, 1;\n\t"
-            "@kill mov.u32 ehi, 0;\n\t"
-            "or.pred act, act, take;\n\t"
-            "bra.uni SEL_TRIP;\n\t"
-            "SEL_NEXT:\n\t"                    // nothing left in the window beats the root, and the root only grows
-            "add.u32 wpos, wpos, 32;\n\t"
-            "setp.lt.s32 inq, wpos, %4;\n\t"
-            "@inq bra.uni SEL_LOAD;\n\t"
-            "mov.u32 drain, %7;\n\t"           // no sift-down takes more than `depth` half-steps
-            "SEL_DRAIN:\n\t"
-            SEL_HALF_STEP
-            SEL_CHILDREN
-            "sub.u32 drain, drain, 1;\n\t"
-            "setp.gt.s32 inq, drain, 0;\n\t"
-            "@inq bra.uni SEL_DRAIN;\n\t"
-            "}\n\t"
-            : "+r"(cnt), "+r"(trips)
-            : "r"(heap_saddr), "r"(queue_saddr), "r"(qn), "r"(consumed), "r"(lane), "r"(depth)
-            : "memory");
+        if (WARPSYNC)
+            asm volatile(SEL_LOOP_ASM("bar.warp.sync 0xffffffff;\n\t")
+                         : "+r"(cnt), "+r"(trips)
+                         : "r"(heap_saddr), "r"(queue_saddr), "r"(qn), "r"(consumed), "r"(lane), "r"(depth)
+                         : "memory");
+        else
+            asm volatile(SEL_LOOP_ASM("")
+                         : "+r"(cnt), "+r"(trips)
+                         : "r"(heap_saddr), "r"(queue_saddr), "r"(qn), "r"(consumed), "r"(lane), "r"(depth)
+                         : "memory");
         __syncwarp();
     }
     trips_out = trips;
@@ -768,7 +781,7 @@ __device__ __forceinline__ int sel_replay_smem(uint32_t heap_saddr, uint32_t que
 }
 
 // generic body shared by the pipeline kernel and the debug entry point
-template <bool SMEM>
+template <bool SMEM, bool WARPSYNC = true>
 __device__ __forceinline__ void heap_select_body(const uint32_t* __restrict__ area, int ncomp, int K, int thres,
                                                   const HeapMem<SMEM> heap, uint32_t* __restrict__ mark_out /* |= 1<<31 */,
                                                   uint8_t* __restrict__ kept_bytes /* or nullptr */,
@@ -883,7 +896,7 @@ __device__ __forceinline__ void heap_select_body(const uint32_t* __restrict__ ar
             int nops = 0;
             if (SMEM) {
                 long long trips = 0;
-                nops = sel_replay_smem(heap.s, (uint32_t)__cvta_generic_to_shared(s_queue), qn, consumed, 32 - __clz(K), lane, trips);
+                nops = sel_replay_smem<WARPSYNC>(heap.s, (uint32_t)__cvta_generic_to_shared(s_queue), qn, consumed, 32 - __clz(K), lane, trips);
                 pn_iter += trips;
             } else {
             bool act = false;
@@ -984,7 +997,8 @@ __global__ void __launch_bounds__(1024) k_cca_select(CcaParams cp, uint32_t* __r
         HeapMem<true> hm;
         hm.g = nullptr;
         hm.s = (uint32_t)__cvta_generic_to_shared(sel_smem + SEL_CHUNK * 8);
-        heap_select_body<true>(area, ct->ncomp, cp.K, cp.thres, hm, area, nullptr, s_queue, &ct->dbg_ops, prof);
+        if (cp.sel_sync) heap_select_body<true, true>(area, ct->ncomp, cp.K, cp.thres, hm, area, nullptr, s_queue, &ct->dbg_ops, prof);
+        else heap_select_body<true, false>(area, ct->ncomp, cp.K, cp.thres, hm, area, nullptr, s_queue, &ct->dbg_ops, prof);
     } else {
         HeapMem<false> hm;
         hm.g = heap_global + (size_t)b * ((cp.K + 3) & ~1);
