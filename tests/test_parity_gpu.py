@@ -551,3 +551,25 @@ def test_preemptive(checker, case):
             assert (gc[f] == cl[f]).all(), "round %d: cluster field %s" % (round_, f)
         if round_ == 0 and kind != "noise":
             assert (want != plain).any(), "the case does not exercise the option"
+
+
+@pytest.mark.parametrize("K", [900, 3500, 5000])
+def test_fused_prepare_tail(checker, K):
+    """Batches of one or two images: the last CTA of every assign+update launch does the bookkeeping of the next pass
+    (prepare_in_tail, K <= 4096; larger K keeps the k_prepare launch).  Labels and Cluster bytes against the compiled
+    reference for one and two images per call, cold and warm start."""
+    from fast_slic_b200 import Engine
+    H, W = 240, 320
+    for B in (1, 2):
+        eng = Engine(H, W, K, B)
+        p = eng.params(10.0, 0.1, 3, True, 10)
+        imgs = np.stack([make_image("syn" if b == 0 else "blocks", H, W, seed=500 + 3 * b + K) for b in range(B)])
+        cl = eng.initialize_clusters_host(imgs)
+        refcl = [checker.initialize(imgs[b], K) for b in range(B)]
+        for round_ in range(2):
+            lab = eng.iterate_host(imgs, cl, p)
+            for b in range(B):
+                want = checker.iterate(imgs[b], refcl[b], 10, 10.0, 0.1, 3, True)
+                assert (lab[b].view(np.uint16) == want).all(), (K, B, round_, b)
+                assert cl[b].tobytes() == refcl[b].tobytes(), (K, B, round_, b)
+        eng.close()

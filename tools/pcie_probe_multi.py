@@ -17,7 +17,13 @@ numa = bind_to_gpu_numa_node(lr)
 if world > 1:
     dist.init_process_group("gloo")
 n, m = 90 * 1000 * 1000, 60 * 1000 * 1000
-h_in = torch.empty(n, dtype=torch.uint8).pin_memory(); d_in = torch.empty(n, dtype=torch.uint8, device="cuda")
+WC = "--wc" in sys.argv  # upload source in write-combined pinned memory (cudaHostAllocWriteCombined): no CPU-cache snoops
+if WC:
+    from cuda.bindings import runtime as rt
+    err, wc_ptr = rt.cudaHostAlloc(n, rt.cudaHostAllocWriteCombined)
+    assert err == rt.cudaError_t.cudaSuccess, err
+d_in = torch.empty(n, dtype=torch.uint8, device="cuda")
+h_in = None if WC else torch.empty(n, dtype=torch.uint8).pin_memory()
 h_out = torch.empty(m, dtype=torch.uint8).pin_memory(); d_out = torch.empty(m, dtype=torch.uint8, device="cuda")
 s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
 
@@ -25,7 +31,10 @@ s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
 def rounds(k):
     for _ in range(k):
         with torch.cuda.stream(s1):
-            d_in.copy_(h_in, non_blocking=True)
+            if WC:
+                rt.cudaMemcpyAsync(d_in.data_ptr(), wc_ptr, n, rt.cudaMemcpyKind.cudaMemcpyHostToDevice, s1.cuda_stream)
+            else:
+                d_in.copy_(h_in, non_blocking=True)
         with torch.cuda.stream(s2):
             h_out.copy_(d_out, non_blocking=True)
     torch.cuda.synchronize()
@@ -47,7 +56,7 @@ for r in range(world):   # one rank at a time
 if world > 1:
     dist.barrier()
 together = timed()
-line = "rank %d (%s): alone %.3f ms/round (H2D %.1f + D2H %.1f GB/s) | all %d ranks at once %.3f ms/round (H2D %.1f + D2H %.1f GB/s)" % (
+line = ("[write-combined upload buffer] " if WC else "") + "rank %d (%s): alone %.3f ms/round (H2D %.1f + D2H %.1f GB/s) | all %d ranks at once %.3f ms/round (H2D %.1f + D2H %.1f GB/s)" % (
     rank, numa, 1e3 * solo, n / solo / 1e9, m / solo / 1e9, world, 1e3 * together, n / together / 1e9, m / together / 1e9)
 if world > 1:
     out = [None] * world
