@@ -1033,23 +1033,38 @@ __device__ __forceinline__ bool cca_is_kept(uint32_t a, int sel_mode, int keep_t
 // (both kernels walk the ncomp components of an image in chunks of 1024 with a small grid: ncomp is a few
 //  thousand for real images, and it is only known on the device)
 #define CCA_KEPT_GRID 16
+// (four 1024-component chunks per trip: the loads of a trip are in flight together and the block-wide bookkeeping is
+//  paid once per trip -- with one chunk per trip both kernels were a chain of load -> barrier round trips)
+#define CCA_KEPT_U 4
 __global__ void __launch_bounds__(CCA_BLOCK) k_kept_count(CcaParams cp, const uint32_t* __restrict__ carea_all,
                                                           const CcaCounters* __restrict__ counters,
                                                           int* __restrict__ blkcnt) {
-    __shared__ int s_cnt;
+    __shared__ int s_cnt[CCA_KEPT_U];
     const int b = blockIdx.y;
     if (cca_skip_image(cp, &counters[b])) return;
     const int ncomp = counters[b].ncomp;
     const int sel_mode = counters[b].sel_mode, keep_thres = counters[b].keep_thres;
-    for (int blk = blockIdx.x; blk * CCA_BLOCK < ncomp; blk += gridDim.x) {
-        if (threadIdx.x == 0) s_cnt = 0;
+    const uint32_t* carea = carea_all + (size_t)b * cp.N;
+    for (int blk0 = blockIdx.x * CCA_KEPT_U; blk0 * CCA_BLOCK < ncomp; blk0 += gridDim.x * CCA_KEPT_U) {
+        if (threadIdx.x < CCA_KEPT_U) s_cnt[threadIdx.x] = 0;
+        uint32_t a[CCA_KEPT_U];
+#pragma unroll
+        for (int u = 0; u < CCA_KEPT_U; u++) {
+            const int c = (blk0 + u) * CCA_BLOCK + threadIdx.x;
+            a[u] = (c < ncomp) ? carea[c] : 0u;
+        }
         __syncthreads();
-        const int c = blk * CCA_BLOCK + threadIdx.x;
-        const bool kept = (c < ncomp) && cca_is_kept(carea_all[(size_t)b * cp.N + c], sel_mode, keep_thres);
-        const unsigned m = __ballot_sync(FSLIC_FULL, kept);
-        if ((threadIdx.x & 31) == 0 && m) atomicAdd(&s_cnt, __popc(m));
+#pragma unroll
+        for (int u = 0; u < CCA_KEPT_U; u++) {
+            const int c = (blk0 + u) * CCA_BLOCK + threadIdx.x;
+            const bool kept = (c < ncomp) && cca_is_kept(a[u], sel_mode, keep_thres);
+            const unsigned m = __ballot_sync(FSLIC_FULL, kept);
+            if ((threadIdx.x & 31) == 0 && m) atomicAdd(&s_cnt[u], __popc(m));
+        }
         __syncthreads();
-        if (threadIdx.x == 0) blkcnt[(size_t)b * cp.nblk + blk] = s_cnt;
+        if (threadIdx.x < CCA_KEPT_U && (blk0 + threadIdx.x) * CCA_BLOCK < ncomp)
+            blkcnt[(size_t)b * cp.nblk + blk0 + threadIdx.x] = s_cnt[threadIdx.x];
+        __syncthreads();  // s_cnt is zeroed again at the top of the next trip
     }
 }
 
@@ -1058,34 +1073,52 @@ __global__ void __launch_bounds__(CCA_BLOCK) k_kept_label(CcaParams cp, const ui
                                                           const CcaCounters* __restrict__ counters,
                                                           const int* __restrict__ blkoff,
                                                           uint16_t* __restrict__ cnew_all) {
-    __shared__ int s_warp[32];
+    __shared__ int s_warp[CCA_KEPT_U][32];
     const int b = blockIdx.y;
     if (cca_skip_image(cp, &counters[b])) return;
     const int ncomp = counters[b].ncomp;
     const int sel_mode = counters[b].sel_mode, keep_thres = counters[b].keep_thres;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int blk = blockIdx.x; blk * CCA_BLOCK < ncomp; blk += gridDim.x) {
-        const int c = blk * CCA_BLOCK + tid;
-        const bool kept = (c < ncomp) && cca_is_kept(carea_all[(size_t)b * cp.N + c], sel_mode, keep_thres);
-        const unsigned m = __ballot_sync(FSLIC_FULL, kept);
-        __syncthreads();  // s_warp of the previous chunk has been read
-        if (lane == 0) s_warp[warp] = __popc(m);
+    const uint32_t* carea = carea_all + (size_t)b * cp.N;
+    for (int blk0 = blockIdx.x * CCA_KEPT_U; blk0 * CCA_BLOCK < ncomp; blk0 += gridDim.x * CCA_KEPT_U) {
+        uint32_t a[CCA_KEPT_U];
+        int off[CCA_KEPT_U];
+#pragma unroll
+        for (int u = 0; u < CCA_KEPT_U; u++) {
+            const int c = (blk0 + u) * CCA_BLOCK + tid;
+            a[u] = (c < ncomp) ? carea[c] : 0u;
+            off[u] = ((blk0 + u) * CCA_BLOCK < ncomp) ? blkoff[(size_t)b * cp.nblk + blk0 + u] : 0;
+        }
+        unsigned m[CCA_KEPT_U];
+        bool kept[CCA_KEPT_U];
+        __syncthreads();  // s_warp of the previous trip has been read
+#pragma unroll
+        for (int u = 0; u < CCA_KEPT_U; u++) {
+            const int c = (blk0 + u) * CCA_BLOCK + tid;
+            kept[u] = (c < ncomp) && cca_is_kept(a[u], sel_mode, keep_thres);
+            m[u] = __ballot_sync(FSLIC_FULL, kept[u]);
+            if (lane == 0) s_warp[u][warp] = __popc(m[u]);
+        }
         __syncthreads();
-        if (warp == 0) {
-            int w = s_warp[lane];
+        if (warp < CCA_KEPT_U) {  // warp u scans the 32 warp counts of chunk u
+            const int w = s_warp[warp][lane];
             int x = w;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                int y = __shfl_up_sync(FSLIC_FULL, x, o);
+                const int y = __shfl_up_sync(FSLIC_FULL, x, o);
                 if (lane >= o) x += y;
             }
-            s_warp[lane] = x - w;
+            s_warp[warp][lane] = x - w;
         }
         __syncthreads();
-        if (c < ncomp) {
-            uint16_t v = 0xFFFF;
-            if (kept) v = (uint16_t)(blkoff[(size_t)b * cp.nblk + blk] + s_warp[warp] + __popc(m & ((1u << lane) - 1)));
-            cnew_all[(size_t)b * cp.N + c] = v;
+#pragma unroll
+        for (int u = 0; u < CCA_KEPT_U; u++) {
+            const int c = (blk0 + u) * CCA_BLOCK + tid;
+            if (c < ncomp) {
+                uint16_t v = 0xFFFF;
+                if (kept[u]) v = (uint16_t)(off[u] + s_warp[u][warp] + __popc(m[u] & ((1u << lane) - 1)));
+                cnew_all[(size_t)b * cp.N + c] = v;
+            }
         }
     }
 }
