@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(256) k_ccl_flatten(CcaParams cp, const uint16_
     int* par = par_all + (size_t)b * cp.N;
     int p[4], sl[4], root[4];
     unsigned m[4], rmask[4];
-    bool ok[4], start[4];
+    bool ok[4], start[4], col0[4];
     int jcol = (blockIdx.x * CCA_BLOCK + w * 128 + lane) % cp.W;  // column of chunk 0; the others by stepping
 #pragma unroll
     for (int r = 0; r < 4; r++) {
@@ -249,6 +249,7 @@ __global__ void __launch_bounds__(256) k_ccl_flatten(CcaParams cp, const uint16_
         const uint32_t v = ok[r] ? lab[p[r]] : 0x10000u;
         const uint32_t left = __shfl_up_sync(FSLIC_FULL, v, 1);
         const int j = jcol;
+        col0[r] = j == 0;
         jcol += 32;
         if (jcol >= cp.W) jcol = (cp.W >= 32) ? (jcol - cp.W) : (jcol % cp.W);
         start[r] = (lane == 0) || (j == 0) || (v != left);
@@ -308,7 +309,10 @@ __global__ void __launch_bounds__(256) k_ccl_flatten(CcaParams cp, const uint16_
 #pragma unroll
     for (int r = 0; r < 4; r++) {
         const int base = __shfl_sync(FSLIC_FULL, incl - mine, w * 4 + r);
-        if ((rmask[r] >> lane) & 1u) rootbuf[base + __popc(rmask[r] & ((1u << lane) - 1u))] = p[r];
+        // bit 31: the root sits in column 0 (k_cca_absorb then looks above instead of left, cca.cpp:243-246, without
+        // dividing by W once per hop)
+        if ((rmask[r] >> lane) & 1u)
+            rootbuf[base + __popc(rmask[r] & ((1u << lane) - 1u))] = p[r] | (col0[r] ? (int)0x80000000 : 0);
     }
     if (threadIdx.x == 31) blkcnt[(size_t)b * cp.nblk + blockIdx.x] = incl;
 }
@@ -406,7 +410,7 @@ __global__ void __launch_bounds__(CCA_BLOCK) k_ccl_number(CcaParams cp, const in
             const int total = __shfl_sync(FSLIC_FULL, incl, 31);
             const int nb_here = min(32, NB - sub);
             for (int r0 = 0; r0 < total; r0 += 32 * NU) {
-                int pp[NU], cc[NU];
+                int pp[NU], cc[NU];  // root pixel (bit 31: its column-0 flag; -1: none), component number
                 uint32_t aa[NU];
 #pragma unroll
                 for (int u = 0; u < NU; u++) {
@@ -417,19 +421,19 @@ __global__ void __launch_bounds__(CCA_BLOCK) k_ccl_number(CcaParams cp, const in
                     const int bincl = __shfl_sync(FSLIC_FULL, incl, bi), bcnt = __shfl_sync(FSLIC_FULL, mycnt, bi);
                     const int boff = __shfl_sync(FSLIC_FULL, myoff, bi);
                     const int t = r - (bincl - bcnt);
-                    pp[u] = -1;
+                    pp[u] = -1;  // (never a root entry: pixel indices stay below 2^30)
                     if (r < total) {
                         pp[u] = rootbuf_all[(size_t)b * cp.N + (size_t)(blk0 + sub + bi) * CCA_BLOCK + t];
                         cc[u] = boff + t;
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < NU; u++) aa[u] = pp[u] >= 0 ? aux[pp[u]] : 0u;
+                for (int u = 0; u < NU; u++) aa[u] = pp[u] != -1 ? aux[pp[u] & 0x7fffffff] : 0u;
 #pragma unroll
                 for (int u = 0; u < NU; u++) {
                     uint32_t bin = 0xffffffffu;  // not a candidate
-                    if (pp[u] >= 0) {
-                        aux[pp[u]] = (uint32_t)cc[u];  // the area slot of a root now holds its component number
+                    if (pp[u] != -1) {
+                        aux[pp[u] & 0x7fffffff] = (uint32_t)cc[u];  // the area slot of a root now holds its component number
                         cleader_all[(size_t)b * cp.N + cc[u]] = pp[u];
                         carea_all[(size_t)b * cp.N + cc[u]] = aa[u];
                         // histogram of candidate areas: bins 0..2047 exact, bin 2048 = "2048 or more" (k_cca_threshold)
@@ -1145,12 +1149,12 @@ __global__ void __launch_bounds__(256) k_cca_absorb(CcaParams cp, const int* __r
             lab = 0;
             break;
         }
-        const int l = cleader[c];
-        const int q = (l % cp.W > 0) ? (l - 1) : (l - cp.W);
+        const int lf = cleader[c], l = lf & 0x7fffffff;  // bit 31: the leader sits in column 0
+        const int q = (lf >= 0) ? (l - 1) : (l - cp.W);
         c = (int)aux[par[q]];  // component of the neighbour; strictly smaller than c
         lab = cnew[c];
     }
-    final_all[(size_t)b * cp.N + cleader[c0]] = lab;
+    final_all[(size_t)b * cp.N + (cleader[c0] & 0x7fffffff)] = lab;
     }
 }
 

@@ -1,5 +1,5 @@
 """Summarise an ncu report per CUDA source line (all source files of the kernel):
-python tools/ncu_lines.py report.ncu-rep [min_pct] [kernel-index]"""
+python tools/ncu_lines.py report.ncu-rep [min_pct] [kernel-name-substring]   (default: the first kernel of the report)"""
 import csv
 import os
 import subprocess
@@ -7,6 +7,7 @@ import sys
 
 rep = sys.argv[1]
 minpct = float(sys.argv[2]) if len(sys.argv) > 2 else 0.6
+want = sys.argv[3] if len(sys.argv) > 3 else None
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr = rows[0]
@@ -18,7 +19,8 @@ keys = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active', 'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed',
         'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum']
 stall = [h for h in hdr if h.startswith('smsp__average_warps_issue_stalled') and h.endswith('_per_issue_active.ratio')]
-for r in rows[2:3]:
+sel = [r for r in rows[2:] if want is None or want in r[hdr.index('Kernel Name')]][:1]
+for r in sel:
     print('---', r[hdr.index('Kernel Name')][:60])
     for k in keys:
         if k in hdr:
@@ -38,7 +40,7 @@ for r in rows:
         fname = os.path.basename(r[1])
         continue
     if r[0] == 'Function Name':
-        if first_fn is None:
+        if first_fn is None and (want is None or want in r[1]):
             first_fn = r[1]
         cur_fn = r[1]
         continue
