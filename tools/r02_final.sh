@@ -37,3 +37,8 @@ print("D32 value %.0f MP/s  %.3f ms/step | seq %.3f ms | e2e %.0f | assign %.1f 
 PY
 python tools/single_probe.py --one
 python tools/select_probe.py | tail -5
+# summarise on the box (the reports of the stage kernels are too large to travel back) and keep only the assign report
+PROFILES_DIR=$O/profiles_${TAG} bash tools/make_profiles.sh ${TAG} ${TAG} > $O/make_profiles.log 2>&1
+tail -3 $O/make_profiles.log
+rm -f $O/${TAG}_stages_b32.ncu-rep $O/${TAG}_stages_D8.ncu-rep $O/${TAG}_assign5_D8.ncu-rep
+du -sh $O
