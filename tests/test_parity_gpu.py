@@ -573,3 +573,22 @@ def test_fused_prepare_tail(checker, K):
                 assert (lab[b].view(np.uint16) == want).all(), (K, B, round_, b)
                 assert cl[b].tobytes() == refcl[b].tobytes(), (K, B, round_, b)
         eng.close()
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_configurations(checker, seed):
+    """Seeded random shapes (widths that are and are not multiples of 8: TMA and LDG assign kernels), K, compactness,
+    min_size_factor, stride, Lab on/off, iteration counts, image kinds: every stage against the compiled reference,
+    cold start and warm start."""
+    rng = np.random.RandomState(7000 + seed)
+    H = int(rng.randint(24, 420))
+    W = int(rng.randint(3, 70)) * 8 if seed % 2 == 0 else int(rng.randint(24, 560))
+    K = int(rng.randint(1, max(2, H * W // 60)))
+    kind = ["syn", "noise", "blocks", "syn"][seed % 4]
+    args = dict(max_iter=int(rng.randint(0, 13)), compactness=float(rng.choice([0.5, 3.0, 10.0, 40.0])),
+                min_size_factor=float(rng.choice([0.0, 0.1, 0.25, 1.0])), subsample_stride=int(rng.choice([1, 2, 3, 3, 3, 5])),
+                convert_to_lab=bool(rng.randint(0, 2)))
+    img = make_image(kind, H, W, seed=900 + seed, sigma=float(rng.choice([5.0, 12.0, 30.0])))
+    name = "seed%d %dx%d K%d %s %r" % (seed, H, W, K, kind, args)
+    _compare(name, _run_cuda(img, K, args), _run_oracle(checker, img, K, args))
+    _compare(name + " warm", _run_cuda(img, K, args, iterate_twice=True), _run_oracle(checker, img, K, args, iterate_twice=True))
