@@ -296,6 +296,7 @@ static int create_impl(int device, int H, int W, int K, int max_batch, bool cca_
     CKC(dalloc(&c->blkcnt, bc * nblk));
     CKC(dalloc(&c->blkoff, bc * nblk));
     CKC(dalloc(&c->counters, bc));
+    CKC(cudaMemset(c->counters, 0, bc * sizeof(CcaCounters)));  // the diagnostics entry may read them before the first run
     CKC(dalloc(&c->ahist, bc * CCA_HIST));
     c->heap_K = 65536 + 8;
     CKC(dalloc(&c->heap, bc * (size_t)c->heap_K));
