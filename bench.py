@@ -522,7 +522,9 @@ def main():
     roofline = {"kernel": kernel_name, "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "bytes_per_launch": alg_bytes, "avg_launch_us": avg_ms * 1e3,
-                "launches_timed": k_n, "stage_ms_last_step": stage, "cca_stage_ms_last_step": cca_stage}
+                "launches_timed": k_n, "stage_ms_last_step": stage}
+    if any(v > 0 for v in cca_stage.values()):  # the connectivity sub-stages are only timed for batches below 4 (one stream)
+        roofline["cca_stage_ms_last_step"] = cca_stage
 
     # ---- end to end through the public API with HOST buffers (H2D + compute + D2H inside the timed region) ----
     slic = Slic(num_components=K, compactness=COMPACTNESS, min_size_factor=msf, subsample_stride=STRIDE)
