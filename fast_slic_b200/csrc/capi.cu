@@ -91,7 +91,7 @@ struct fslic_ctx {
     uint32_t* carea = nullptr;     // [Bc][N]
     uint16_t* cnew = nullptr;      // [Bc][N]
     uint16_t* fin = nullptr;       // [Bc][N]  (second half of the cnew allocation)
-    int* rootbuf = nullptr;        // [Bc][N] ordered root lists of k_ccl_flatten; ALIASES cnew + fin (dead until the tail)
+    int* rootbuf = nullptr;        // [Bc][N] ordered root lists of k_ccl_flatten
     int* blkcnt = nullptr;         // [Bc][nblk]
     int* blkoff = nullptr;         // [Bc][nblk]
     CcaCounters* counters = nullptr;  // [Bc]
@@ -104,6 +104,9 @@ struct fslic_ctx {
     uint16_t* d_lab = nullptr;
     cudaStream_t own_stream = nullptr, in_stream = nullptr, out_stream = nullptr, side_stream = nullptr;
     cudaEvent_t side_fork = nullptr, side_join = nullptr, tail_done = nullptr;
+    // second lane of the blocking host path (the two halves of a batch overlap on the device)
+    cudaStream_t own_stream2 = nullptr, side_stream2 = nullptr;
+    cudaEvent_t side_fork2 = nullptr, side_join2 = nullptr, tail_done2 = nullptr, front_done = nullptr;
     // the `preemptive` option (preempt.cuh), allocated at the first such call
     uint8_t* pre_cellmap = nullptr;     // [B][ceil(H/2S) * ceil(W/2S)] active 2S x 2S cells
     int* pre_nactive = nullptr;         // [B] active clusters
@@ -186,7 +189,7 @@ extern "C" int fslic_b200_destroy(fslic_ctx* c) {
     DeviceGuard dev_guard__(c->device);
     void* ptrs[] = {c->d_gamma, c->d_labtbl, c->quad,   c->labels,  c->cinfo,  c->acc,    c->cell_start,
                     c->cinfo_tmp, c->cell_cnt, c->prep_tickets, c->sptable, c->par,  c->aux,    c->cleader, c->carea,
-                    c->cnew,    c->blkcnt, c->blkoff,  c->counters, c->ahist, c->heap, c->d_img,
+                    c->cnew,    c->rootbuf, c->blkcnt, c->blkoff,  c->counters, c->ahist, c->heap, c->d_img,
                     c->d_cl,    c->d_lab};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -202,6 +205,10 @@ extern "C" int fslic_b200_destroy(fslic_ctx* c) {
     if (c->side_fork) cudaEventDestroy(c->side_fork);
     if (c->side_join) cudaEventDestroy(c->side_join);
     if (c->tail_done) cudaEventDestroy(c->tail_done);
+    if (c->own_stream2) cudaStreamDestroy(c->own_stream2);
+    if (c->side_stream2) cudaStreamDestroy(c->side_stream2);
+    for (cudaEvent_t e : {c->side_fork2, c->side_join2, c->tail_done2, c->front_done})
+        if (e) cudaEventDestroy(e);
     if (c->gexec) cudaGraphExecDestroy(c->gexec);
     if (c->h_counters) cudaFreeHost(c->h_counters);
     if (c->selprof) cudaFree(c->selprof);
@@ -274,8 +281,8 @@ static int create_impl(int device, int H, int W, int K, int max_batch, bool cca_
         CKC(dalloc(&c->sptable, (size_t)2 * SPT_MAX_ELEMS));
     }
 
-    // CCA scratch: 22 B/pixel/image; cap the resident set at ~12 GB
-    const size_t per_img = N * 22 + 4096;
+    // CCA scratch: 26 B/pixel/image; cap the resident set at ~12 GB
+    const size_t per_img = N * 26 + 4096;
     size_t bc = (12ull << 30) / per_img;
     if (bc < 1) bc = 1;
     if (bc > B) bc = B;
@@ -292,7 +299,7 @@ static int create_impl(int device, int H, int W, int K, int max_batch, bool cca_
     CKC(dalloc(&c->carea, bc * N));
     CKC(dalloc(&c->cnew, 2 * bc * N));
     c->fin = c->cnew + bc * N;
-    c->rootbuf = reinterpret_cast<int*>(c->cnew);
+    CKC(dalloc(&c->rootbuf, bc * N));  // (its own array: two halves of a batch may be in different phases at the same time)
     CKC(dalloc(&c->blkcnt, bc * nblk));
     CKC(dalloc(&c->blkoff, bc * nblk));
     CKC(dalloc(&c->counters, bc));
@@ -309,6 +316,12 @@ static int create_impl(int device, int H, int W, int K, int max_batch, bool cca_
     CKC(cudaEventCreateWithFlags(&c->side_fork, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&c->side_join, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&c->tail_done, cudaEventDisableTiming));
+    CKC(cudaStreamCreateWithFlags(&c->own_stream2, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&c->side_stream2, cudaStreamNonBlocking));
+    CKC(cudaEventCreateWithFlags(&c->side_fork2, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&c->side_join2, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&c->tail_done2, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&c->front_done, cudaEventDisableTiming));
     CKC(cudaMallocHost(reinterpret_cast<void**>(&c->h_counters), 64 * sizeof(CcaCounters)));
     if (const char* e = getenv("FSLIC_SELPROF")) {
         if (atoi(e) != 0) {
@@ -404,9 +417,31 @@ struct HostOut {
     bool done;               // set when run_cca issued the label copies itself
 };
 
+// `slot` / `lane`: the blocking host path runs the two halves of a batch as two independent calls that overlap on the
+// device; each gets its own window of the scratch arrays (images slot .. slot + batch) and its own side stream / events.
 static int run_cca(fslic_ctx* c, const uint16_t* d_in, uint16_t* d_out, int batch, int K, int thres, cudaStream_t st,
-                   int* launches, HostOut* ho = nullptr) {
+                   int* launches, HostOut* ho = nullptr, int slot = 0, int lane = 0) {
     const int N = c->N;
+    if (slot != 0 && slot + batch > c->cca_batch) return set_err(FSLIC_EINVAL, "scratch window out of range");
+    const size_t so = (size_t)slot;
+    const int nblk_all = ceil_div(N, CCA_BLOCK);
+    int* const x_par = c->par + so * N;
+    uint32_t* const x_aux = c->aux + so * N;
+    int* const x_cleader = c->cleader + so * N;
+    uint32_t* const x_carea = c->carea + so * N;
+    uint16_t* const x_cnew = c->cnew + so * N;
+    uint16_t* const x_fin = c->fin + so * N;
+    int* const x_rootbuf = c->rootbuf + so * N;
+    int* const x_blkcnt = c->blkcnt + so * nblk_all;
+    int* const x_blkoff = c->blkoff + so * nblk_all;
+    CcaCounters* const x_counters = c->counters + so;
+    unsigned int* const x_ahist = c->ahist + so * CCA_HIST;
+    unsigned long long* const x_heap = c->heap + so * (size_t)c->heap_K;
+    long long* const x_selprof = c->selprof ? c->selprof + 8 * so : nullptr;
+    CcaCounters* const x_hcnt = c->h_counters + so;
+    cudaStream_t const x_side = lane ? c->side_stream2 : c->side_stream;
+    cudaEvent_t const x_fork = lane ? c->side_fork2 : c->side_fork, x_join = lane ? c->side_join2 : c->side_join,
+                      x_tail = lane ? c->tail_done2 : c->tail_done;
     CcaParams cp;
     cp.H = c->H; cp.W = c->W; cp.N = N; cp.K = K; cp.thres = thres; cp.which = -1;
     cp.nblk = ceil_div(N, CCA_BLOCK);
@@ -422,32 +457,32 @@ static int run_cca(fslic_ctx* c, const uint16_t* d_in, uint16_t* d_out, int batc
         const bool timed = c->cca_timing && nb < 4 && batch <= c->cca_batch;  // one stream, one sub-batch
         c->cca_timed = timed;
         if (timed) CK(cudaEventRecord(c->cev[0], st));
-        CK(cudaMemsetAsync(c->counters, 0, sizeof(CcaCounters) * nb, st));
-        CK(cudaMemsetAsync(c->ahist, 0, sizeof(unsigned int) * CCA_HIST * nb, st));
+        CK(cudaMemsetAsync(x_counters, 0, sizeof(CcaCounters) * nb, st));
+        CK(cudaMemsetAsync(x_ahist, 0, sizeof(unsigned int) * CCA_HIST * nb, st));
         dim3 g(cp.nblk, nb);
         {
             const int ttx = ceil_div(c->W, CCL_T), tty = ceil_div(c->H, CCL_T);
             const long ntt = (long)ttx * tty * nb;
-            k_ccl_tile<<<(int)((ntt + CCL_TW - 1) / CCL_TW), 32 * CCL_TW, 0, st>>>(cp, in, c->par, c->aux, ttx, tty, ntt);
+            k_ccl_tile<<<(int)((ntt + CCL_TW - 1) / CCL_TW), 32 * CCL_TW, 0, st>>>(cp, in, x_par, x_aux, ttx, tty, ntt);
         }
         {
             const int seam_px = ((c->W - 1) / CCL_T) * c->H + ((c->H - 1) / CCL_T) * c->W;
             if (seam_px > 0) {
                 dim3 gs(ceil_div(seam_px, 256), nb);
-                k_ccl_seams<<<gs, 256, 0, st>>>(cp, in, c->par);
+                k_ccl_seams<<<gs, 256, 0, st>>>(cp, in, x_par);
             }
         }
         if (timed) CK(cudaEventRecord(c->cev[1], st));
-        k_ccl_flatten<<<g, 256, 0, st>>>(cp, in, c->par, c->aux, c->blkcnt, c->rootbuf);
-        k_scan_blocks<<<nb, 1024, 0, st>>>(c->blkcnt, c->blkoff, cp.nblk, cp.nblk, nullptr, 0, 1,
-                                           &c->counters[0].ncomp, (int)(sizeof(CcaCounters) / sizeof(int)), nullptr, -1);
+        k_ccl_flatten<<<g, 256, 0, st>>>(cp, in, x_par, x_aux, x_blkcnt, x_rootbuf);
+        k_scan_blocks<<<nb, 1024, 0, st>>>(x_blkcnt, x_blkoff, cp.nblk, cp.nblk, nullptr, 0, 1,
+                                           &x_counters[0].ncomp, (int)(sizeof(CcaCounters) / sizeof(int)), nullptr, -1);
         // grids of the per-component walks: sized for full batches (a few CTAs per image); a small batch gets more
         // CTAs per image instead, it is all dependent-load latency there
         const int number_grid = nb >= 8 ? CCA_NUMBER_GRID : std::min(std::max(ceil_div(cp.nblk, 32), CCA_NUMBER_GRID), 64);
-        k_ccl_number<<<dim3(number_grid, nb), CCA_BLOCK, 0, st>>>(cp, c->rootbuf, c->aux, c->blkcnt, c->blkoff, c->cleader, c->carea,
-                                                                      c->counters, c->ahist);
+        k_ccl_number<<<dim3(number_grid, nb), CCA_BLOCK, 0, st>>>(cp, x_rootbuf, x_aux, x_blkcnt, x_blkoff, x_cleader, x_carea,
+                                                                      x_counters, x_ahist);
         if (timed) CK(cudaEventRecord(c->cev[2], st));
-        k_cca_threshold<<<nb, 1024, 0, st>>>(cp, c->carea, c->counters, c->ahist);
+        k_cca_threshold<<<nb, 1024, 0, st>>>(cp, x_carea, x_counters, x_ahist);
         if (timed) CK(cudaEventRecord(c->cev[3], st));
         // Everything after the threshold decision depends on the kept set.  For images k_cca_threshold settled
         // that is known now; for the (few) images whose ties need the sequential std::partial_sort replay it
@@ -458,43 +493,43 @@ static int run_cca(fslic_ctx* c, const uint16_t* d_in, uint16_t* d_out, int batc
             CcaParams cq = cp;
             cq.which = which;
             const dim3 gk(std::min(cp.nblk, std::max(CCA_KEPT_GRID, 256 / nb)), nb);
-            k_kept_count<<<gk, CCA_BLOCK, 0, ts>>>(cq, c->carea, c->counters, c->blkcnt);
-            k_scan_blocks<<<nb, 1024, 0, ts>>>(c->blkcnt, c->blkoff, cp.nblk, 0, &c->counters[0].ncomp,
+            k_kept_count<<<gk, CCA_BLOCK, 0, ts>>>(cq, x_carea, x_counters, x_blkcnt);
+            k_scan_blocks<<<nb, 1024, 0, ts>>>(x_blkcnt, x_blkoff, cp.nblk, 0, &x_counters[0].ncomp,
                                                (int)(sizeof(CcaCounters) / sizeof(int)), CCA_BLOCK,
-                                               &c->counters[0].nkept, (int)(sizeof(CcaCounters) / sizeof(int)),
-                                               c->counters, which);
-            k_kept_label<<<gk, CCA_BLOCK, 0, ts>>>(cq, c->carea, c->counters, c->blkoff, c->cnew);
+                                               &x_counters[0].nkept, (int)(sizeof(CcaCounters) / sizeof(int)),
+                                               x_counters, which);
+            k_kept_label<<<gk, CCA_BLOCK, 0, ts>>>(cq, x_carea, x_counters, x_blkoff, x_cnew);
             int ab = ceil_div(N, 256 * (nb < 4 ? 2 : 8));
             if (ab > c->num_sms * 8) ab = c->num_sms * 8;
             dim3 ga(ab, nb);
             if (timed) cudaEventRecord(c->cev[4], ts);
-            k_cca_absorb<<<ga, 256, 0, ts>>>(cq, c->par, c->aux, c->cleader, c->cnew, c->counters, c->fin);
+            k_cca_absorb<<<ga, 256, 0, ts>>>(cq, x_par, x_aux, x_cleader, x_cnew, x_counters, x_fin);
             if (timed) cudaEventRecord(c->cev[5], ts);
             int ob = ceil_div(ceil_div(N, 8), 256);  // 8 pixels per thread on the vector path (any N works: grid-stride)
             if (ob > c->num_sms * 32) ob = c->num_sms * 32;
             dim3 go(ob, nb);
-            k_cca_output<<<go, 256, 0, ts>>>(cq, c->par, c->fin, out, c->counters);
+            k_cca_output<<<go, 256, 0, ts>>>(cq, x_par, x_fin, out, x_counters);
             if (timed) cudaEventRecord(c->cev[6], ts);
         };
         const bool split = nb >= 4;
         const bool early = split && ho && batch <= c->cca_batch && nb <= 64;
         if (early) {
             // the host path is synchronous anyway: wait for the threshold decision and read the per-image flags
-            CK(cudaMemcpyAsync(c->h_counters, c->counters, sizeof(CcaCounters) * nb, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(x_hcnt, x_counters, sizeof(CcaCounters) * nb, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
         }
         if (split) {
-            CK(cudaEventRecord(c->side_fork, st));
-            CK(cudaStreamWaitEvent(c->side_stream, c->side_fork, 0));
-            tail(0, c->side_stream);
-            CK(cudaEventRecord(c->side_join, c->side_stream));
+            CK(cudaEventRecord(x_fork, st));
+            CK(cudaStreamWaitEvent(x_side, x_fork, 0));
+            tail(0, x_side);
+            CK(cudaEventRecord(x_join, x_side));
         }
         auto copy_runs = [&](int want) -> int {  // D2H of maximal runs of images whose need_sim flag == want
             int b = 0;
             while (b < nb) {
-                if ((c->h_counters[b].need_sim != 0) != (want != 0)) { b++; continue; }
+                if ((x_hcnt[b].need_sim != 0) != (want != 0)) { b++; continue; }
                 int e = b;
-                while (e < nb && (c->h_counters[e].need_sim != 0) == (want != 0)) e++;
+                while (e < nb && (x_hcnt[e].need_sim != 0) == (want != 0)) e++;
                 CK(cudaMemcpyAsync(ho->h_labels + (size_t)b * N, out + (size_t)b * N, (size_t)(e - b) * N * 2,
                                    cudaMemcpyDeviceToHost, ho->out_stream));
                 b = e;
@@ -502,21 +537,21 @@ static int run_cca(fslic_ctx* c, const uint16_t* d_in, uint16_t* d_out, int batc
             return FSLIC_OK;
         };
         if (early) {
-            CK(cudaStreamWaitEvent(ho->out_stream, c->side_join, 0));
+            CK(cudaStreamWaitEvent(ho->out_stream, x_join, 0));
             int rc2 = copy_runs(0);
             if (rc2) return rc2;
         }
-        k_cca_select<<<nb, 1024, SEL_CHUNK * 8 + (cp.heap_in_smem ? heap_bytes : 0), st>>>(cp, c->carea, c->counters, c->heap, c->selprof);
+        k_cca_select<<<nb, 1024, SEL_CHUNK * 8 + (cp.heap_in_smem ? heap_bytes : 0), st>>>(cp, x_carea, x_counters, x_heap, x_selprof);
         tail(split ? 1 : -1, st);
         if (early) {
-            CK(cudaEventRecord(c->tail_done, st));
-            CK(cudaStreamWaitEvent(ho->out_stream, c->tail_done, 0));
+            CK(cudaEventRecord(x_tail, st));
+            CK(cudaStreamWaitEvent(ho->out_stream, x_tail, 0));
             int rc2 = copy_runs(1);
             if (rc2) return rc2;
             ho->done = true;
         }
         if (split) {
-            CK(cudaStreamWaitEvent(st, c->side_join, 0));
+            CK(cudaStreamWaitEvent(st, x_join, 0));
             if (launches) *launches += 5;
         }
         CK(cudaGetLastError());
@@ -993,9 +1028,9 @@ static int iterate_front(fslic_ctx* c, int b0, const uint8_t* d_images, fslic_cl
 
 // Back half (context.cpp:191-194): connectivity enforcement of images [0, batch) of c->labels into d_labels.
 static int iterate_back(fslic_ctx* c, uint16_t* d_labels, int batch, const fslic_params* p, cudaStream_t st, int* launches,
-                        HostOut* ho = nullptr) {
+                        HostOut* ho = nullptr, int slot = 0, int lane = 0) {
     const int thres = (int)round((double)(c->S * c->S) * (double)p->min_size_factor);  // context.cpp:16
-    return run_cca(c, c->labels, d_labels, batch, c->K, thres, st, launches, ho);
+    return run_cca(c, c->labels + (size_t)slot * c->N, d_labels, batch, c->K, thres, st, launches, ho, slot, lane);
 }
 
 static int iterate_graphed(fslic_ctx* c, const uint8_t* d_images, fslic_cluster* d_clusters, uint16_t* d_labels, int batch,
@@ -1299,6 +1334,58 @@ static int iterate_host_enqueue_body(fslic_ctx* c, const uint8_t* h_images, fsli
             c->kev_on = false;  // per-launch kernel timing belongs to fslic_b200_iterate(collect_timing >= 2) only
             c->kev_used = 0;
             const int h0 = nb / 2;
+            static const bool no_lanes = getenv("FSLIC_HOST_LANES") && atoi(getenv("FSLIC_HOST_LANES")) == 0;
+            if (may_sync && !no_lanes && nchunks == 1 && nb >= 16 && nb <= c->cca_batch && nb <= 64) {
+                // Blocking call: the caller waits anyway, so the two halves run as two independent pipelines that overlap
+                // on the device -- half A's connectivity stage (incl. the ~0.7 ms std::partial_sort replay of its ambiguous
+                // images, a handful of SMs) and its label download run while half B is still on the wire / in its assign
+                // passes.  Each half has its own compute + side stream and its own window of the scratch arrays.
+                for (int hpart = 0; hpart < 2; hpart++) {
+                    const int s0 = b0 + (hpart ? h0 : 0), sn = hpart ? nb - h0 : h0;
+                    CK(cudaMemcpyAsync(c->d_img + (size_t)s0 * N * 3, h_images + (size_t)s0 * N * 3, (size_t)sn * N * 3,
+                                       cudaMemcpyHostToDevice, c->in_stream));
+                    CK(cudaMemcpyAsync(c->d_cl + (size_t)s0 * c->K, h_clusters + (size_t)s0 * c->K,
+                                       (size_t)sn * c->K * sizeof(fslic_cluster), cudaMemcpyHostToDevice, c->in_stream));
+                    CK(cudaEventRecord(hpart ? c->pipe_ev[3 * k] : c->pipe_ev[3 * k + 2], c->in_stream));
+                }
+                for (int hpart = 0; hpart < 2; hpart++) {  // both front halves first: nothing in them waits for the host
+                    const int s0 = b0 + (hpart ? h0 : 0), sn = hpart ? nb - h0 : h0;
+                    cudaStream_t cs = hpart ? c->own_stream2 : c->own_stream;
+                    CK(cudaStreamWaitEvent(cs, hpart ? c->pipe_ev[3 * k] : c->pipe_ev[3 * k + 2], 0));
+                    // (the second front half starts behind the first: they share the cached spatial patches, which the first
+                    //  call may still be building, and the first half's data is there earlier anyway)
+                    if (hpart) CK(cudaStreamWaitEvent(cs, c->front_done, 0));
+                    rc = iterate_front(c, s0 - b0, c->d_img + (size_t)s0 * N * 3, c->d_cl + (size_t)s0 * c->K, sn, &pp, coef, cs,
+                                       &launches, false);
+                    if (rc) return rc;
+                    if (!hpart) CK(cudaEventRecord(c->front_done, cs));
+                }
+                for (int hpart = 0; hpart < 2; hpart++) {  // back halves: each reads its per-image decisions back mid-way
+                    const int s0 = b0 + (hpart ? h0 : 0), sn = hpart ? nb - h0 : h0;
+                    cudaStream_t cs = hpart ? c->own_stream2 : c->own_stream;
+                    HostOut ho;
+                    ho.h_labels = h_labels + (size_t)s0 * N;
+                    ho.out_stream = c->out_stream;
+                    ho.done = false;
+                    rc = iterate_back(c, c->d_lab + (size_t)s0 * N, sn, &pp, cs, &launches, &ho, s0 - b0, hpart);
+                    if (rc) return rc;
+                    // clusters of this half (and its labels if run_cca did not download them itself)
+                    CK(cudaEventRecord(c->pipe_ev[3 * k + 1], cs));
+                    CK(cudaStreamWaitEvent(c->out_stream, c->pipe_ev[3 * k + 1], 0));
+                    if (!ho.done)
+                        CK(cudaMemcpyAsync(h_labels + (size_t)s0 * N, c->d_lab + (size_t)s0 * N, (size_t)sn * N * 2,
+                                           cudaMemcpyDeviceToHost, c->out_stream));
+                    CK(cudaMemcpyAsync(h_clusters + (size_t)s0 * c->K, c->d_cl + (size_t)s0 * c->K,
+                                       (size_t)sn * c->K * sizeof(fslic_cluster), cudaMemcpyDeviceToHost, c->out_stream));
+                }
+                c->last_launches = launches;
+                c->pending = true;
+                CK(cudaStreamSynchronize(c->out_stream));
+                CK(cudaStreamSynchronize(c->own_stream));
+                CK(cudaStreamSynchronize(c->own_stream2));
+                c->pending = false;
+                return FSLIC_OK;
+            }
             for (int hpart = 0; hpart < 2; hpart++) {
                 const int s0 = b0 + (hpart ? h0 : 0), sn = hpart ? nb - h0 : h0;
                 CK(cudaMemcpyAsync(c->d_img + (size_t)s0 * N * 3, h_images + (size_t)s0 * N * 3, (size_t)sn * N * 3,
@@ -1381,6 +1468,8 @@ static int iterate_host_enqueue(fslic_ctx* c, const uint8_t* h_images, fslic_clu
         cudaStreamSynchronize(c->in_stream);
         cudaStreamSynchronize(c->own_stream);
         cudaStreamSynchronize(c->side_stream);
+        if (c->own_stream2) cudaStreamSynchronize(c->own_stream2);
+        if (c->side_stream2) cudaStreamSynchronize(c->side_stream2);
         cudaStreamSynchronize(c->out_stream);
         cudaGetLastError();
         c->pending = false;

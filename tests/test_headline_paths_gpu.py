@@ -37,9 +37,10 @@ def batch32(checker):
     return imgs, want
 
 
-@pytest.mark.parametrize("nb", [32, 9])
+@pytest.mark.parametrize("nb", [32, 17, 9])
 def test_blocking_host_call_batch(checker, batch32, nb):
-    """fslic_b200_iterate_host at batch 32 (nb >= 8 branch: split uploads + early D2H) and 9 (odd halves)."""
+    """fslic_b200_iterate_host at batch 32 and 17 (two overlapping half pipelines with their own streams and scratch
+    windows, early D2H per half; 17 = odd halves) and 9 (one pipeline: split uploads + early D2H)."""
     from fast_slic_b200 import Engine
     imgs, want = batch32
     eng = Engine(H, W, K, 32)
