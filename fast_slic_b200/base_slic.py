@@ -429,8 +429,28 @@ class BaseSlic(object):
             images = np.ascontiguousarray(images)
             if images.dtype != np.uint8:
                 raise ValueError("images must be uint8")
+        m = self._slic_model
         with _locked(lambda: get_engine(H, W, K, B, device)) as eng:
-            if is_tensor:
+            if m.real_dist or m.preemptive:
+                # the float-distance contexts and `preemptive` have device entry points only: host batches go up and down here
+                with torch.cuda.device(eng.device):
+                    d_img = images if is_tensor else torch.from_numpy(images).to(eng.device)
+                    if clusters is None:
+                        d_cl = eng.initialize_clusters(d_img)
+                    elif is_tensor:
+                        d_cl = clusters
+                    else:
+                        d_cl = torch.from_numpy(np.ascontiguousarray(clusters).view(np.uint8).reshape(B, K, 32).copy()).to(eng.device)
+                    if m.preemptive:
+                        d_lab = eng.iterate_preemptive(d_img, d_cl, params, m.preemptive_thres)
+                    else:
+                        d_lab = eng.iterate_real(m.real_dist_type, d_img, d_cl, params)
+                    if is_tensor:
+                        labels, clusters = d_lab, d_cl
+                    else:
+                        labels = d_lab.cpu().numpy()
+                        clusters = d_cl.cpu().numpy().view(CLUSTER_DTYPE).reshape(B, K)
+            elif is_tensor:
                 if clusters is None:
                     clusters = eng.initialize_clusters(images)
                 labels = eng.iterate(images, clusters, params)

@@ -592,3 +592,25 @@ def test_random_configurations(checker, seed):
     name = "seed%d %dx%d K%d %s %r" % (seed, H, W, K, kind, args)
     _compare(name, _run_cuda(img, K, args), _run_oracle(checker, img, K, args))
     _compare(name + " warm", _run_cuda(img, K, args, iterate_twice=True), _run_oracle(checker, img, K, args, iterate_twice=True))
+
+
+def test_iterate_batch_variants(checker):
+    """iterate_batch() of the float-distance classes and of Slic(preemptive=True): every image of a host batch and of a
+    device batch equals the single-image result of the compiled reference (the batch entry must not fall back to the
+    default integer path)."""
+    import fast_slic_b200 as fs
+    H, W, K, B = 120, 160, 48, 3
+    imgs = np.stack([make_image("syn" if b != 1 else "blocks", H, W, seed=610 + b) for b in range(B)])
+    for name, obj, ref_call in (
+            ("l2", fs.SlicRealDistL2(num_components=K), lambda im, cl: checker.iterate_real(1, im, cl, 10, 10.0, 0.25, 3, True)),
+            ("noq", fs.SlicRealDistNoQ(num_components=K), lambda im, cl: checker.iterate_real(2, im, cl, 10, 10.0, 0.25, 3, True)),
+            ("preemptive", fs.Slic(num_components=K, preemptive=True, preemptive_thres=0.1),
+             lambda im, cl: checker.iterate(im, cl, 10, 10.0, 0.25, 3, True, preemptive=True, preemptive_thres=0.1))):
+        lab_h, cl_h = obj.iterate_batch(imgs, return_clusters=True)
+        lab_d, cl_d = obj.iterate_batch(torch.from_numpy(imgs).cuda(), return_clusters=True)
+        for b in range(B):
+            cl = checker.initialize(imgs[b], K)
+            want = ref_call(imgs[b], cl)
+            assert (lab_h[b].view(np.uint16) == want).all(), (name, "host", b)
+            assert (lab_d[b].cpu().numpy().view(np.uint16) == want).all(), (name, "device", b)
+            assert cl_h[b].tobytes() == cl.tobytes() == cl_d[b].cpu().numpy().tobytes(), (name, b)
