@@ -394,6 +394,7 @@ class BaseSlic(object):
         return self._last_assignment
 
     def iterate(self, image, max_iter=10):
+        self._slic_model._unsupported()  # (before any device work: LSC etc. fail the same way with or without a GPU)
         if not self._slic_model.initialized:
             self._slic_model.initialize(image)
         assignment = self._slic_model.iterate(image, max_iter, self.compactness, self.min_size_factor,
@@ -494,6 +495,12 @@ class SlicRealDistNoQ(SlicRealDist):
         float_color = kwargs.pop("float_color", True)
         super(SlicRealDistNoQ, self).__init__(*args, **kwargs)
         self._slic_model.float_color = float_color
+
+
+class LSC(SlicRealDist):
+    """== fast_slic.base_slic.LSC (base_slic.py:87-89), kept so that `from fast_slic import LSC` keeps importing: linear
+    spectral clustering is a different algorithm (src/lsc.cpp) outside this engine -- iterate() raises NotImplementedError."""
+    real_dist_type = "lsc"
 
 
 def enforce_connectivity(assignments, min_threshold, device=0):

@@ -373,3 +373,15 @@ def test_oracle_preemptive_matches_compiled_reference(port, ref):
                 assert (p1 == p2).all() and (o1 == o2).all() and c1.tobytes() == c2.tobytes(), (kind, H, W, K, thres, arch, round_)
                 if round_ == 0:
                     assert (o2 != plain).any(), "the case does not exercise the option"
+
+
+def test_import_compatibility_classes():
+    """`from fast_slic import LSC` / `from fast_slic.avx2 import SlicAvx2, LSCAvx2` (fast_slic/base_slic.py:87-89,
+    fast_slic/avx2.py:10-14) keep importing from this package; LSC is outside the engine and says so at iterate()."""
+    import fast_slic_b200 as fs
+    from fast_slic_b200.avx2 import LSCAvx2, SlicAvx2
+    assert issubclass(SlicAvx2, fs.Slic) and issubclass(LSCAvx2, fs.LSC) and issubclass(fs.LSC, fs.SlicRealDist)
+    assert SlicAvx2(num_components=7).slic_model.num_components == 7
+    for cls in (fs.LSC, LSCAvx2):
+        with pytest.raises(NotImplementedError):
+            cls(num_components=5).iterate(np.zeros((8, 8, 3), np.uint8))
