@@ -143,6 +143,14 @@ class SlicModel(object):
         result.initialized = self.initialized
         return result
 
+    def to_yxmrgb(self):
+        """== cfast_slic.SlicModel.to_yxmrgb (cfast_slic.pyx:100-113): float [K, 6] rows (y, x, num_members, r, g, b)."""
+        c = self._clusters
+        out = np.empty((self._num_components, 6), dtype=float)
+        for col, name in enumerate(("y", "x", "num_members", "r", "g", "b")):
+            out[:, col] = c[name]
+        return out
+
     @property
     def clusters(self):
         """cfast_slic.pyx:51-66."""

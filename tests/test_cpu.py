@@ -385,3 +385,14 @@ def test_import_compatibility_classes():
     for cls in (fs.LSC, LSCAvx2):
         with pytest.raises(NotImplementedError):
             cls(num_components=5).iterate(np.zeros((8, 8, 3), np.uint8))
+
+
+def test_slic_model_to_yxmrgb():
+    """cfast_slic.pyx:100-113: float64 [K, 6] = (y, x, num_members, r, g, b) per cluster."""
+    import fast_slic_b200 as fs
+    m = fs.SlicModel(3)
+    m._clusters["y"], m._clusters["x"], m._clusters["num_members"] = [1, 2, 3], [4, 5, 6], [7, 8, 9]
+    m._clusters["r"], m._clusters["g"], m._clusters["b"] = [10, 11, 12], [13, 14, 15], [16, 17, 18]
+    out = m.to_yxmrgb()
+    assert out.dtype == np.float64 and out.shape == (3, 6)
+    assert out.tolist() == [[1, 4, 7, 10, 13, 16], [2, 5, 8, 11, 14, 17], [3, 6, 9, 12, 15, 18]]
